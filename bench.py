@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""DPV hot-path benchmark (contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): default_stereo, batch 8 per GPU, D=64 bins, image
+256x384, features / cost volume 64x96, C=67 channels, V=1 source view, fp32.  One "step" pushes
+one batch of 8 frames through the hot-path kernels (cost volume, 1/4-res log-softmax, full-res
+head with E[d]/Var/argmax/hand-off, uncertainty field); the CNN blocks between them are cuDNN's
+and are not part of the path (their outputs are synthetic inputs here).
+`value`  : frames/s with every input already resident in HBM, device-timed, max over ranks.
+`e2e`    : frames/s through the host-buffer C-ABI pipeline (dpv_pipeline_run): pinned host
+           inputs are copied in, results copied back, inside the timed region.
+`roofline`: the dominant kernel (full-res head) against the measured HBM peak.
+`cpu_baseline` / --impl reference: the CPU port of the reference's PyTorch path (oracle/) on the
+           host cores, bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DPV frames/sec (D=64, 256x384)"
+UNIT = "frames/s"
+WL = dict(B=8, V=1, C=67, D=64, h=64, w=96, H=256, W=384)
+WORKLOAD = "default_stereo: batch 8/GPU, D=64, image 256x384, features 64x96, C=67, V=1"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def host_inputs(dpv, batch, seed=0):
+    s = dpv.synth
+    d = s.depth_candidates(5.0, 40.0, WL["D"], 1.0)
+    cam = s.camera(WL["w"], WL["h"], batch)
+    feats = s.randn(seed + 1, batch, WL["V"] + 1, WL["C"], WL["h"], WL["w"])
+    poses = s.stereo_poses(batch)
+    logits = s.ground_plane_logits(seed + 2, batch, WL["H"], WL["W"], d, cam["intrinsics_up"][0])
+    return dict(d=d, feats=feats, poses=poses, K=cam["intrinsics"], rays=cam["unit_ray"],
+                intr_up=cam["intrinsics_up"], logits=logits)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (NVML, ~10 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, nm in names.items():
+                    if bits & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        return {"sm_mhz": int(statistics.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_port_fps(dpv, budget_s=15.0, frames_per_step=1, max_steps=50, warmup=1):
+    """The reference's CPU PyTorch path (oracle port), frames/s on this host's cores."""
+    from oracle import dpv_oracle as O
+    T = torch.from_numpy
+    torch.set_num_threads(os.cpu_count() or 1)
+    hi = host_inputs(dpv, frames_per_step, seed=100)
+
+    def one_step():
+        for b in range(frames_per_step):
+            O.frame_hot_path(T(hi["feats"][b:b + 1, -1]), T(hi["feats"][b:b + 1, :-1]), hi["d"],
+                             T(hi["poses"][b, :-1, :3, :3]), T(hi["poses"][b, :-1, :3, 3]),
+                             T(hi["K"][b]), T(hi["rays"][b]), 10.0, None, T(hi["logits"][b:b + 1]),
+                             T(hi["intr_up"][b]))
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_steps:
+        one_step()
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return n * frames_per_step / dt, n, dt
+
+
+def run_reference(args, dpv):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import dpv_oracle as O
+    T = torch.from_numpy
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = 1                                  # bounded sample: 1 frame of the batch per step
+    hi = host_inputs(dpv, frames, seed=100)
+
+    def one_step():
+        for b in range(frames):
+            O.frame_hot_path(T(hi["feats"][b:b + 1, -1]), T(hi["feats"][b:b + 1, :-1]), hi["d"],
+                             T(hi["poses"][b, :-1, :3, :3]), T(hi["poses"][b, :-1, :3, 3]),
+                             T(hi["K"][b]), T(hi["rays"][b]), 10.0, None, T(hi["logits"][b:b + 1]),
+                             T(hi["intr_up"][b]))
+    steps = min(args.steps, 40)                 # keep the whole run within minutes
+    for _ in range(min(args.warmup, 3)):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    fps = steps * frames / dt
+    sample = "%d step(s) x %d frame of the batch-8 workload, torch CPU ops, %d threads" % (steps, frames, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, dpv):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the DPV path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frame_mod = importlib.import_module("probabilistic-depth_b200.frame")
+    pipe_mod = importlib.import_module("probabilistic-depth_b200.pipeline")
+    B = WL["B"]
+    hi = host_inputs(dpv, B, seed=rank)
+    step = frame_mod.FrameStep(B, WL["V"], WL["C"], WL["D"], WL["h"], WL["w"], WL["H"], WL["W"], hi["d"],
+                               sigma=10.0, mode="default", device=dev)
+    # two input sets in HBM, alternated: 2 x 227 MB read + 227 MB written per step >> 126 MB L2
+    nset = 2
+    dsets = []
+    for i in range(nset):
+        h = hi if i == 0 else host_inputs(dpv, B, seed=rank + 1000 * i)
+        dsets.append({k: torch.from_numpy(np.ascontiguousarray(h[k])).to(dev)
+                      for k in ("feats", "poses", "K", "rays", "logits", "intr_up")})
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    cur = {"i": 0, "on": False}
+
+    def hook(which):
+        if cur["on"]:
+            ev[cur["i"]][which].record()
+
+    def one(i, timed=False):
+        s = dsets[i % nset]
+        cur["i"], cur["on"] = i, timed
+        step.run(s["feats"], s["poses"], s["K"], s["rays"], s["logits"], s["intr_up"], head_hook=hook)
+
+    for i in range(max(args.warmup, 3)):
+        one(i)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = dpv._lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        one(i, timed=True)
+    t_end.record()
+    barrier()
+    launches = dpv._lib.launch_count() - l0
+    ms = t_start.elapsed_time(t_end)
+    head_ms = [a.elapsed_time(b) for a, b in ev]
+
+    # ---- end to end through the host-buffer pipeline --------------------------------------
+    pipe = pipe_mod.FramePipeline(B, WL["V"], WL["C"], WL["D"], WL["h"], WL["w"], WL["H"], WL["W"],
+                                  device=local)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(hi[k])).pin_memory()
+           for k in ("feats", "poses", "K", "rays", "logits", "intr_up")}
+    outs = pipe.outputs(pinned=True)
+    e2e_steps = max(3, min(args.steps, 30))
+
+    def e2e_one():
+        pipe.run(pin["feats"], pin["poses"], pin["K"], pin["rays"], hi["d"], pin["logits"],
+                 pin["intr_up"], 10.0, outs)
+    for _ in range(3):
+        e2e_one()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_one()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d, d2h = pipe.last_bytes()
+    clocks = sampler.finish()
+    pipe.close()
+
+    # ---- max over ranks ---------------------------------------------------------------------
+    stats = torch.tensor([ms, e2e_s, statistics.mean(head_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms, e2e_s, head_mean_ms = [float(v) for v in stats.cpu()]
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        alg = step.algorithmic_bytes()
+        head_bytes = alg["head_full"]
+        achieved = head_bytes / (head_mean_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "head_full_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (2 alternating 227 MB sets)",
+                       "kernels_per_step": step.launches_per_step(),
+                       "algorithmic_bytes_per_step": alg,
+                       "frame_hbm_frac": sum(alg.values()) / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "roofline": {"kernel": "dpv::head_kernel<64,2> (full-res head)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": head_bytes, "ms_per_launch": head_mean_ms},
+            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "dpv_pipeline_run (host buffers, pinned)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import warnings
+            warnings.filterwarnings("ignore")
+            fps, n, dt = cpu_port_fps(dpv)
+            line["cpu_baseline"] = {
+                "value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "sample": "%d frame(s) of the batch-8 workload in %.1f s, torch CPU ops" % (n, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    dpv = importlib.import_module("probabilistic-depth_b200")
+    if args.impl == "reference":
+        run_reference(args, dpv)
+    else:
+        run_ours(args, dpv)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+/*
+ * dpv_b200.h -- C ABI of libdpv_sm100a.so, the B200 (sm_100a) implementation of the
+ * depth-probability-volume (DPV) hot path of soulslicer/probabilistic-depth.
+ *
+ * The reference has no FFI for this path (it is Python calling PyTorch ATen ops); the one
+ * native binding it does have is correlation_cuda.forward(...)
+ * (models/correlation_package/correlation_cuda.cc:10-16,169-172).  The entry points below
+ * are what a cffi / ctypes / pybind binding for the path would bind, one per reference
+ * function; each comment names the reference site it replaces (paths relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *  - All buffers are DEVICE pointers to contiguous fp32 (row-major, NCHW-style) unless a
+ *    parameter says otherwise; the caller owns every allocation, the library never
+ *    allocates on the data path (dpv_pipeline_* owns its staging buffers) and never syncs.
+ *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns.
+ *  - Return value: 0 on success, a positive cudaError_t on a CUDA failure, a negative
+ *    DPV_E_* code on a bad argument.  dpv_error_string() explains either.
+ *  - Inputs are never modified.  No global mutable state; safe to call from one host thread
+ *    per device/stream.
+ *  - There is no CPU implementation behind any of these.
+ */
+#ifndef DPV_B200_H_
+#define DPV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPV_E_BADARG   (-1)   /* null pointer, non-positive dimension, ... */
+#define DPV_E_UNSUPP   (-2)   /* dimension outside what the kernels were built for */
+#define DPV_E_NODEVICE (-3)   /* no sm_100 device / image not loadable */
+
+#define DPV_DIST_L2 0         /* warping/homography.py:80-82 */
+#define DPV_DIST_L1 1         /* warping/homography.py:84-86 */
+
+/* Input interpretation of the depth-bin axis for dpv_head / dpv_ufield. */
+#define DPV_IN_LOGITS 0       /* un-normalised scores: log-softmax is applied        */
+#define DPV_IN_LOGPROB 1      /* already log-probabilities (BV_log=True)             */
+#define DPV_IN_PROB 2         /* linear probabilities (BV_log=False)                 */
+
+int dpv_abi_version(void);
+const char* dpv_error_string(int code);
+/* Number of kernel launches this library has enqueued since load (for gpu_launches). */
+long long dpv_launch_count(void);
+
+/* ---- K1 + K2a : plane-sweep cost volume ------------------------------------------------
+ * Replaces est_swp_volume_v4 (warping/homography.py:98-135) including
+ * _back_warp_homo_parallel (:170-198), the D-fold .repeat (:123), F.grid_sample (:197) and
+ * img_dis_L2_pard / img_dis_L1_pard (:80-86), batched over B items and V source views in
+ * one launch (the reference loops over items in Python, models/models.py:528-550).
+ *
+ *   cost[b,k,y,x] = sum_v ( sum_c dist( bilinear(src[b,v,c], P(b,v,k,y,x)) - ref[b,c,y,x] ) ) / sigma
+ *   P = K t + (K R ray) d_k ;  u,v = P_xy / (P_z + 1e-10) ;  grid = ((u-cx)/cx, (v-cy)/cy) ;
+ *   bilinear, zeros padding, align_corners=False.  Non-finite coordinates sample 0.
+ *
+ * ref   : item b at ref + b*ref_bstride,                      [C,H,W]
+ * src   : view v of item b at src + b*src_bstride + v*src_vstride, [C,H,W]
+ * pose  : 4x4 row-major [R|t] of view v of item b at pose + b*pose_bstride + v*16
+ * K     : 3x3 row-major intrinsics of item b at K + b*k_bstride   (k_bstride may be 0)
+ * rays  : [3, H*W] unit rays of item b at rays + b*rays_bstride   (rays_bstride may be 0)
+ * d_candi : [D] fp32 depth of each plane
+ * cost  : [B, D, H, W] out
+ * log_softmax_out : optional [B, D, H, W]; when non-null additionally receives
+ *         log_softmax(cost, dim=1) (models/packnet.py:394 places them back to back).
+ * algo  : 0 = choose, 1 = direct per-plane gather, 2 = per-cell Gram form (L2 only).
+ */
+int dpv_sweep_cost_volume(const float* ref, const float* src, const float* pose, const float* K,
+                          const float* rays, const float* d_candi, float* cost,
+                          float* log_softmax_out,
+                          int B, int V, int C, int D, int H, int W,
+                          int64_t ref_bstride, int64_t src_bstride, int64_t src_vstride,
+                          int64_t pose_bstride, int64_t k_bstride, int64_t rays_bstride,
+                          float sigma, int dist, int algo, void* stream);
+
+/* ---- K1 stand-alone : per-plane warp ----------------------------------------------------
+ * Replaces _back_warp_homo_parallel (warping/homography.py:170-198) for callers that want
+ * the warped stack itself.  img [N or 1, C, H, W] (img_nstride = 0 broadcasts one image over
+ * the planes instead of the reference's .repeat), term1 [3], term2 [3, H*W], d [N];
+ * out [N, C, H, W].  cx, cy as the reference reads them from intrinsic_M.
+ */
+int dpv_warp_planes(const float* img, const float* d, const float* term1, const float* term2,
+                    float* out, int N, int C, int H, int W, int64_t img_nstride,
+                    float cx, float cy, void* stream);
+
+/* ---- K4a : diagonal feature warp --------------------------------------------------------
+ * Replaces warp_feature (warping/homography.py:137-168): out[b,v,k] = channel k of view v
+ * warped onto plane k.  feat [B,V,D,H,W] -> out [B,V,D,H,W]; pose/K/rays as above.
+ */
+int dpv_warp_feature(const float* feat, const float* pose, const float* K, const float* rays,
+                     const float* d_candi, float* out, int B, int V, int D, int H, int W,
+                     int64_t pose_bstride, int64_t k_bstride, int64_t rays_bstride, void* stream);
+
+/* ---- K3 (+K4b) : depth-bin head ---------------------------------------------------------
+ * One pass over x [B,D,H,W] producing any subset of (null pointer = skip):
+ *   logp     [B,D,H,W]  log_softmax(x (+ addend), dim=1)     models/models.py:351,560,637; :694 with addend
+ *   prob     [B,D,H,W]  exp(logp)                             models/models.py:653,675,697
+ *   depth    [B,H,W]    sum_k d_k exp(logp_k), fp32           utils/img_utils.py:52-61
+ *   variance [B,H,W]    sum_k (d_k-mean)^2 p_k, fp32          trainer/default_trainer.py:333-336 (f64 there)
+ *   argmax   [B,H,W]    int64 first maximal bin of logp       (torch.argmax; not in the reference)
+ *   quarter  [B,D,H/4,W/4] logp at rows/cols 0,4,8,...        trainer/default_trainer.py:221-222
+ * in_mode: DPV_IN_LOGITS / DPV_IN_LOGPROB / DPV_IN_PROB (the last two skip the soft-max;
+ * logp then echoes log-probabilities).  addend may be null.  d_candi [D] fp32.
+ */
+int dpv_head(const float* x, const float* addend, const float* d_candi,
+             float* logp, float* prob, float* depth, float* variance, int64_t* argmax,
+             float* quarter, int B, int D, int H, int W, int in_mode, void* stream);
+
+/* ---- K4c : LiDAR prior and Bayesian fusion ----------------------------------------------
+ * dpv_lidar_prior replaces gen_dpv_withmask (utils/img_utils.py:360-375, :31-50):
+ *   dmaps [B,H,W], masks [B,H,W] -> prior [B,D,H,W] clamped to [2.2e-16, 1].
+ * two_sigma_sq is 2*pow(sqrt(var),2) evaluated in fp32 by the caller as the reference does.
+ * dpv_bayes_fuse replaces models/models.py:669-672: fused = clamp(normalise(exp(bv + log prior)));
+ *   the prior is either given (prior != null) or generated on the fly from dmaps/masks.
+ *   Outputs fused [B,D,H,W] and/or log_fused [B,D,H,W].
+ */
+int dpv_lidar_prior(const float* dmaps, const float* masks, const float* d_candi, float* prior,
+                    int B, int D, int H, int W, float two_sigma_sq, void* stream);
+int dpv_bayes_fuse(const float* bv, const float* prior, const float* dmaps, const float* masks,
+                   const float* d_candi, float* fused, float* log_fused,
+                   int B, int D, int H, int W, float two_sigma_sq, void* stream);
+
+/* ---- K5 : uncertainty-field collapse ----------------------------------------------------
+ * Replaces gen_ufield (utils/img_utils.py:268-358), batched.  dpv [B,D,H,W] in `in_mode`
+ * (DPV_IN_LOGPROB or DPV_IN_PROB); depth [B,H,W] = E[d] of that DPV (dpv_head's `depth`
+ * output); intr_up 3x3 per item (bstride may be 0); mask [B,H,W] optional.
+ * pad_depth: E[d] of an all-zero (padding) DPV column as the reference would compute it:
+ * sum_k d_k in log mode (exp(0) = 1 per bin), 0 in linear mode.
+ * row_fwd/row_inv [H], col_fwd/col_inv [W]: int32 source index of the +pshift / -pshift
+ * nearest-neighbour shifts (-1 = samples zero padding), built once per shape by the host
+ * wrapper from the reference's own grid construction.
+ * Outputs uf [B,D,W] (0/0 = NaN as in the reference) and depth_zero [B,H,W].
+ * workspace: dpv_ufield_workspace_floats(B, D, H, W) floats.
+ */
+int64_t dpv_ufield_workspace_floats(int B, int D, int H, int W);
+int dpv_ufield(const float* dpv, const float* depth, const float* d_candi, const float* intr_up,
+               const float* mask, const int* row_fwd, const int* row_inv, const int* col_fwd,
+               const int* col_inv, float* uf, float* depth_zero, float* workspace,
+               int B, int D, int H, int W, int64_t intr_bstride, int in_mode,
+               float zstart, float zend, float maxd, float mind, float pad_depth,
+               void* stream);
+
+/* ---- K2b : local correlation ------------------------------------------------------------
+ * Replaces correlation_cuda.forward (models/correlation_package/correlation_cuda.cc:10-87,
+ * kernel correlation_cuda_kernel.cu:41-114) and models/correlation_native.py:13-23 for
+ * kernel_size=1, stride1=stride2=1, pad_size=max_displacement:
+ *   out[b,(i*(2r+1)+j),y,x] = (1/C) sum_c x1[b,c,y,x] * x2[b,c,y+i-r,x+j-r]   (zero padded)
+ * x1, x2 [B,C,H,W] -> out [B,(2r+1)^2,H,W].
+ */
+int dpv_correlation(const float* x1, const float* x2, float* out, int B, int C, int H, int W,
+                    int max_displacement, void* stream);
+
+/* ---- depth-plane sharding (large D) -----------------------------------------------------
+ * Soft-max over planes that live on several GPUs (not in the reference).  Rank g
+ * owns planes [plane_offset, plane_offset + D) of x [B, D, HW].  Sequence per rank, with the
+ * host issuing the collectives (NCCL over NVLink) on the same stream between the calls:
+ *   dpv_shard_max      -> all-reduce MAX of local_max [B*HW]        (local_argmax: all-gather)
+ *   dpv_shard_sums     -> all-reduce SUM of sums [2, B*HW]  (sum exp(x-M), sum d exp(x-M))
+ *   dpv_shard_central  -> all-reduce SUM of central [B*HW]  (sum (d-E)^2 exp(x-M)), optional
+ *   dpv_shard_finish   -> logp = x - M - log S for the local planes; depth, variance replicated
+ *   dpv_shard_argmax_merge: first-max-wins merge of the gathered (value, index) candidates.
+ */
+int dpv_shard_max(const float* x, float* local_max, float* local_argmax, int B, int D, int HW,
+                  int plane_offset, void* stream);
+int dpv_shard_sums(const float* x, const float* d_local, const float* global_max, float* sums,
+                   int B, int D, int HW, void* stream);
+int dpv_shard_central(const float* x, const float* d_local, const float* global_max,
+                      const float* global_sums, float* central, int B, int D, int HW, void* stream);
+int dpv_shard_finish(const float* x, const float* global_max, const float* global_sums,
+                     const float* global_central, float* logp, float* depth, float* variance,
+                     int B, int D, int HW, void* stream);
+int dpv_shard_argmax_merge(const float* vals, const float* idx, int64_t* out, int G, int64_t n,
+                           void* stream);
+
+/* ---- whole-frame host pipeline (end-to-end with HOST buffers) ---------------------------
+ * What a non-PyTorch host (the reference's ROS node, ros/ros_net.py:241-303) would call: one
+ * object owning device staging buffers, streams and events; run() takes pinned or pageable
+ * HOST pointers, overlaps H2D copies, kernels and D2H copies item by item and returns when
+ * the results are in host memory.  Stages: cost volume -> log-softmax (1/4 res) -> full-res
+ * head -> uncertainty field (the `default` / stereo frame of SURVEY.md section 8).
+ */
+typedef struct dpv_pipeline dpv_pipeline;
+int dpv_pipeline_create(dpv_pipeline** out, int device, int B, int V, int C, int D,
+                        int h, int w, int H, int W);
+int dpv_pipeline_destroy(dpv_pipeline* p);
+/* Host inputs: feats [B,V+1,C,h,w] (reference view last, models/models.py:531-535),
+ * poses [B,V+1,4,4], K [B,3,3], rays [B,3,h*w], d_candi [D], logits_full [B,D,H,W],
+ * intr_up [B,3,3], shift LUTs as for dpv_ufield.
+ * Host outputs (null = skip): bv [B,D,h,w], depth [B,H,W], variance [B,H,W],
+ * argmax [B,H,W] int64, uf [B,D,W], depth_zero [B,H,W], quarter [B,D,H/4,W/4].
+ * Device-resident result kept for the next frame: the refined log-DPV. */
+int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float* poses, const float* K,
+                     const float* rays, const float* d_candi, const float* logits_full,
+                     const float* intr_up, const int* row_fwd, const int* row_inv,
+                     const int* col_fwd, const int* col_inv, float sigma,
+                     float* bv, float* depth, float* variance, int64_t* argmax, float* uf,
+                     float* depth_zero, float* quarter);
+/* Bytes copied host->device and device->host by the last run(). */
+int dpv_pipeline_last_bytes(const dpv_pipeline* p, int64_t* h2d, int64_t* d2h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPV_B200_H_ */

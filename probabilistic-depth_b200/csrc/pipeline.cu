@@ -1,0 +1,185 @@
+// Whole-frame host pipeline: HOST buffers in, HOST buffers out.
+//
+// What a non-PyTorch caller of the reference's hot path (its ROS node, ros/ros_net.py:241-303,
+// or an eval loop like trainer/default_trainer.py:189-260) would bind: one object that owns the
+// device staging buffers, three streams and per-item events, and pushes a batch of frames
+// through
+//     cost volume (K1+K2a) -> log-softmax at 1/4 res (K3) -> full-res head (K3: log-DPV, E[d],
+//     Var, arg-max, 1/4 hand-off) -> uncertainty field (K5)
+// item by item, so that the H2D copy of item i+1, the kernels of item i and the D2H copy of
+// item i-1 overlap.  The refined log-DPV stays resident on the device (it is the next frame's
+// feedback input, trainer/default_trainer.py:221-222); only the per-frame products travel back.
+#include <new>
+#include <vector>
+
+#include "dpv_common.cuh"
+
+struct dpv_pipeline {
+    int device, B, V, C, D, h, w, H, W;
+    cudaStream_t s_in, s_run, s_out;
+    std::vector<cudaEvent_t> e_in, e_done;
+    cudaEvent_t e_const;
+    // inputs
+    float *feats, *poses, *K, *rays, *d, *logits, *intr;
+    int *row_fwd, *row_inv, *col_fwd, *col_inv;
+    // results
+    float *cost, *bv, *refined, *depth, *var, *uf, *dz, *quarter, *ws;
+    long long* argmax;
+    int64_t ws_floats_per_item;
+    int64_t h2d, d2h;
+};
+
+namespace {
+
+template <typename T>
+cudaError_t dalloc(T** p, int64_t n) { return cudaMalloc((void**)p, (size_t)n * sizeof(T)); }
+
+#define PIPE_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
+#define PIPE_RC(expr) do { int r__ = (expr); if (r__ != 0) return r__; } while (0)
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" int dpv_pipeline_create(dpv_pipeline** out, int device, int B, int V, int C, int D,
+                                   int h, int w, int H, int W) {
+    if (!out || B <= 0 || V <= 0 || C <= 0 || D <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0)
+        return DPV_E_BADARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DPV_E_NODEVICE;
+    DeviceGuard guard(device);
+    dpv_pipeline* p = new (std::nothrow) dpv_pipeline();
+    if (!p) return DPV_E_BADARG;
+    p->device = device; p->B = B; p->V = V; p->C = C; p->D = D; p->h = h; p->w = w; p->H = H; p->W = W;
+    p->h2d = p->d2h = 0;
+    const int64_t hw = (int64_t)h * w, HW = (int64_t)H * W;
+    PIPE_TRY(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+    PIPE_TRY(cudaStreamCreateWithFlags(&p->s_run, cudaStreamNonBlocking));
+    PIPE_TRY(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    p->e_in.resize(B); p->e_done.resize(B);
+    for (int i = 0; i < B; ++i) {
+        PIPE_TRY(cudaEventCreateWithFlags(&p->e_in[i], cudaEventDisableTiming));
+        PIPE_TRY(cudaEventCreateWithFlags(&p->e_done[i], cudaEventDisableTiming));
+    }
+    PIPE_TRY(cudaEventCreateWithFlags(&p->e_const, cudaEventDisableTiming));
+    PIPE_TRY(dalloc(&p->feats, (int64_t)B * (V + 1) * C * hw));
+    PIPE_TRY(dalloc(&p->poses, (int64_t)B * (V + 1) * 16));
+    PIPE_TRY(dalloc(&p->K, (int64_t)B * 9));
+    PIPE_TRY(dalloc(&p->rays, (int64_t)B * 3 * hw));
+    PIPE_TRY(dalloc(&p->d, D));
+    PIPE_TRY(dalloc(&p->logits, (int64_t)B * D * HW));
+    PIPE_TRY(dalloc(&p->intr, (int64_t)B * 9));
+    PIPE_TRY(dalloc(&p->row_fwd, H)); PIPE_TRY(dalloc(&p->row_inv, H));
+    PIPE_TRY(dalloc(&p->col_fwd, W)); PIPE_TRY(dalloc(&p->col_inv, W));
+    PIPE_TRY(dalloc(&p->cost, (int64_t)B * D * hw));
+    PIPE_TRY(dalloc(&p->bv, (int64_t)B * D * hw));
+    PIPE_TRY(dalloc(&p->refined, (int64_t)B * D * HW));
+    PIPE_TRY(dalloc(&p->depth, (int64_t)B * HW));
+    PIPE_TRY(dalloc(&p->var, (int64_t)B * HW));
+    PIPE_TRY(dalloc(&p->argmax, (int64_t)B * HW));
+    PIPE_TRY(dalloc(&p->uf, (int64_t)B * D * W));
+    PIPE_TRY(dalloc(&p->dz, (int64_t)B * HW));
+    PIPE_TRY(dalloc(&p->quarter, (int64_t)B * D * (H / 4) * (W / 4) + 1));
+    p->ws_floats_per_item = dpv_ufield_workspace_floats(1, D, H, W);
+    PIPE_TRY(dalloc(&p->ws, p->ws_floats_per_item * B));
+    *out = p;
+    return 0;
+}
+
+extern "C" int dpv_pipeline_destroy(dpv_pipeline* p) {
+    if (!p) return DPV_E_BADARG;
+    DeviceGuard guard(p->device);
+    cudaStreamSynchronize(p->s_in); cudaStreamSynchronize(p->s_run); cudaStreamSynchronize(p->s_out);
+    void* bufs[] = {p->feats, p->poses, p->K, p->rays, p->d, p->logits, p->intr, p->row_fwd,
+                    p->row_inv, p->col_fwd, p->col_inv, p->cost, p->bv, p->refined, p->depth, p->var,
+                    p->argmax, p->uf, p->dz, p->quarter, p->ws};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (auto e : p->e_in) cudaEventDestroy(e);
+    for (auto e : p->e_done) cudaEventDestroy(e);
+    cudaEventDestroy(p->e_const);
+    cudaStreamDestroy(p->s_in); cudaStreamDestroy(p->s_run); cudaStreamDestroy(p->s_out);
+    delete p;
+    return 0;
+}
+
+extern "C" int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float* poses,
+                                const float* K, const float* rays, const float* d_candi,
+                                const float* logits_full, const float* intr_up, const int* row_fwd,
+                                const int* row_inv, const int* col_fwd, const int* col_inv,
+                                float sigma, float* bv, float* depth, float* variance,
+                                int64_t* argmax, float* uf, float* depth_zero, float* quarter) {
+    if (!p || !feats || !poses || !K || !rays || !d_candi || !logits_full || !intr_up || !row_fwd ||
+        !row_inv || !col_fwd || !col_inv)
+        return DPV_E_BADARG;
+    DeviceGuard guard(p->device);
+    const int B = p->B, V = p->V, C = p->C, D = p->D, h = p->h, w = p->w, H = p->H, W = p->W;
+    const int64_t hw = (int64_t)h * w, HW = (int64_t)H * W;
+    const int64_t q4 = (int64_t)(H / 4) * (W / 4);
+    int64_t in_bytes = 0, out_bytes = 0;
+    auto up = [&](void* dst, const void* src, int64_t bytes) {
+        in_bytes += bytes;
+        return cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, p->s_in);
+    };
+    auto down = [&](void* dst, const void* src, int64_t bytes) {
+        out_bytes += bytes;
+        return cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, p->s_out);
+    };
+    // per-call constants
+    PIPE_TRY(up(p->poses, poses, (int64_t)B * (V + 1) * 16 * 4));
+    PIPE_TRY(up(p->K, K, (int64_t)B * 9 * 4));
+    PIPE_TRY(up(p->rays, rays, (int64_t)B * 3 * hw * 4));
+    PIPE_TRY(up(p->d, d_candi, (int64_t)D * 4));
+    PIPE_TRY(up(p->intr, intr_up, (int64_t)B * 9 * 4));
+    PIPE_TRY(up(p->row_fwd, row_fwd, (int64_t)H * 4)); PIPE_TRY(up(p->row_inv, row_inv, (int64_t)H * 4));
+    PIPE_TRY(up(p->col_fwd, col_fwd, (int64_t)W * 4)); PIPE_TRY(up(p->col_inv, col_inv, (int64_t)W * 4));
+    // sum of the bins = E[d] of a zero-padded log-DPV column (see dpv_ufield)
+    float pad_depth = 0.f;
+    for (int k = 0; k < D; ++k) pad_depth += d_candi[k];
+
+    const int64_t feat_item = (int64_t)(V + 1) * C * hw;
+    for (int i = 0; i < B; ++i) {
+        PIPE_TRY(up(p->feats + i * feat_item, feats + i * feat_item, feat_item * 4));
+        PIPE_TRY(up(p->logits + i * D * HW, logits_full + i * D * HW, (int64_t)D * HW * 4));
+        PIPE_TRY(cudaEventRecord(p->e_in[i], p->s_in));
+        PIPE_TRY(cudaStreamWaitEvent(p->s_run, p->e_in[i], 0));
+        const float* fi = p->feats + i * feat_item;
+        // reference view is the last one (models/models.py:531-535)
+        PIPE_RC(dpv_sweep_cost_volume(fi + (int64_t)V * C * hw, fi, p->poses + (int64_t)i * (V + 1) * 16,
+                                      p->K + i * 9, p->rays + (int64_t)i * 3 * hw, p->d,
+                                      p->cost + (int64_t)i * D * hw, nullptr, 1, V, C, D, h, w,
+                                      0, 0, (int64_t)C * hw, 0, 0, 0, sigma, DPV_DIST_L2, 0, p->s_run));
+        PIPE_RC(dpv_head(p->cost + (int64_t)i * D * hw, nullptr, p->d, p->bv + (int64_t)i * D * hw,
+                         nullptr, nullptr, nullptr, nullptr, nullptr, 1, D, h, w, DPV_IN_LOGITS,
+                         p->s_run));
+        PIPE_RC(dpv_head(p->logits + i * D * HW, nullptr, p->d, p->refined + i * D * HW, nullptr,
+                         p->depth + i * HW, p->var + i * HW, (int64_t*)(p->argmax + i * HW),
+                         p->quarter + i * D * q4, 1, D, H, W, DPV_IN_LOGITS, p->s_run));
+        PIPE_RC(dpv_ufield(p->refined + i * D * HW, p->depth + i * HW, p->d, p->intr + i * 9, nullptr,
+                           p->row_fwd, p->row_inv, p->col_fwd, p->col_inv, p->uf + (int64_t)i * D * W,
+                           p->dz + i * HW, p->ws + i * p->ws_floats_per_item, 1, D, H, W, 0,
+                           DPV_IN_LOGPROB, 0.6f, 0.6f + 0.3f, 100.f, 0.f, pad_depth, p->s_run));
+        PIPE_TRY(cudaEventRecord(p->e_done[i], p->s_run));
+        PIPE_TRY(cudaStreamWaitEvent(p->s_out, p->e_done[i], 0));
+        if (bv) PIPE_TRY(down(bv + (int64_t)i * D * hw, p->bv + (int64_t)i * D * hw, (int64_t)D * hw * 4));
+        if (depth) PIPE_TRY(down(depth + i * HW, p->depth + i * HW, HW * 4));
+        if (variance) PIPE_TRY(down(variance + i * HW, p->var + i * HW, HW * 4));
+        if (argmax) PIPE_TRY(down(argmax + i * HW, p->argmax + i * HW, HW * 8));
+        if (uf) PIPE_TRY(down(uf + (int64_t)i * D * W, p->uf + (int64_t)i * D * W, (int64_t)D * W * 4));
+        if (depth_zero) PIPE_TRY(down(depth_zero + i * HW, p->dz + i * HW, HW * 4));
+        if (quarter) PIPE_TRY(down(quarter + i * D * q4, p->quarter + i * D * q4, (int64_t)D * q4 * 4));
+    }
+    PIPE_TRY(cudaStreamSynchronize(p->s_out));
+    PIPE_TRY(cudaStreamSynchronize(p->s_run));
+    p->h2d = in_bytes; p->d2h = out_bytes;
+    return 0;
+}
+
+extern "C" int dpv_pipeline_last_bytes(const dpv_pipeline* p, int64_t* h2d, int64_t* d2h) {
+    if (!p || !h2d || !d2h) return DPV_E_BADARG;
+    *h2d = p->h2d; *d2h = p->d2h;
+    return 0;
+}

@@ -1,0 +1,109 @@
+"""Device-resident frame step: the hot-path kernels of one batch of frames, back to back.
+
+`FrameStep` pre-allocates every output once and then only enqueues kernels (no allocation, no
+host sync, no Python loop over items), which also makes the step capturable in a CUDA graph.
+Order follows the reference's eval frame (models/models.py:504-565,644-656 and
+trainer/default_trainer.py:221-244,333-336) with the CNN blocks left to cuDNN:
+
+  cost volume  -> log-softmax at 1/4 res  -> [decoder]  -> full-res head  -> uncertainty field
+  (K1+K2a)        (K3)                                     (K3: log-DPV, E[d], Var, argmax,
+                                                            1/4 hand-off)     (K5)
+optionally with the LiDAR fusion (K4c, `upsample`) or the feedback warp + fusion (K4a + K4b,
+`feedback`) between the 1/4-res soft-max and the decoder.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+
+class FrameStep:
+    def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dev = dev
+        self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W = B, V, C, D, h, w, H, W
+        self.mode = mode
+        self.sigma = float(sigma)
+        self.d = ops.depth_bins(d_candi, dev)
+        self.pad_depth = ops._bin_sum(self.d)
+        e = lambda *s, dt=torch.float32: torch.empty(s, device=dev, dtype=dt)
+        self.cost = e(B, D, h, w)
+        self.bv = e(B, D, h, w)
+        self.refined = e(B, D, H, W)
+        self.depth = e(B, H, W)
+        self.var = e(B, H, W)
+        self.argmax = e(B, H, W, dt=torch.int64)
+        self.quarter = e(B, D, H // 4, W // 4)
+        self.uf = e(B, D, W)
+        self.dz = e(B, H, W)
+        self.lib = _lib.load()
+        self.ws = e(int(self.lib.dpv_ufield_workspace_floats(B, D, H, W)))
+        self.luts = ops.shift_luts(H, W, ops.KITTI_UF["pshift"], dev)
+        if mode == "upsample":
+            self.fused = e(B, D, h, w)
+            self.logfused = e(B, D, h, w)
+        if mode == "feedback":
+            self.warped = e(B, V + 1, D, h, w)
+            self.bv_upd = e(B, D, h, w)
+        self.two_sig = ops.two_sigma_sq(0.3)
+        u = ops.KITTI_UF
+        self.uf_params = [float(np.float32(u[k])) for k in ("zstart", "zend", "maxd", "mind")]
+
+    # -- one batch of frames ---------------------------------------------------------------
+    def run(self, feats, poses, K, rays, logits_full, intr_up, dmaps=None, masks=None,
+            feat_raw=None, bv_resi=None, head_hook=None):
+        """feats [B,V+1,C,h,w] (reference view last); poses [B,V+1,4,4]; K [B,3,3]; rays
+        [B,3,h*w]; logits_full [B,D,H,W] (the decoder's pre-softmax output); intr_up [B,3,3].
+        upsample: dmaps [B,h,w], masks [B,1,h,w].  feedback: feat_raw [B,V+1,D,h,w], bv_resi
+        [B,D,h,w] (the 3-D conv residual).  All contiguous fp32 on this device."""
+        B, V, C, D, h, w, H, W = self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W
+        lib, st = self.lib, torch.cuda.current_stream().cuda_stream
+        p = lambda t: None if t is None else t.data_ptr()
+        chw = C * h * w
+        fp = feats.data_ptr()
+        _lib.check(lib.dpv_sweep_cost_volume(
+            fp + 4 * V * chw, fp, p(poses), p(K), p(rays), p(self.d), p(self.cost), None,
+            B, V, C, D, h, w, (V + 1) * chw, (V + 1) * chw, chw, (V + 1) * 16, 9, 3 * h * w,
+            self.sigma, 0, 0, st))
+        _lib.check(lib.dpv_head(p(self.cost), None, p(self.d), p(self.bv), None, None, None, None,
+                                None, B, D, h, w, ops.IN_LOGITS, st))
+        if self.mode == "upsample":
+            _lib.check(lib.dpv_bayes_fuse(p(self.bv), None, p(dmaps), p(masks), p(self.d),
+                                          p(self.fused), p(self.logfused), B, D, h, w, self.two_sig, st))
+        elif self.mode == "feedback":
+            _lib.check(lib.dpv_warp_feature(p(feat_raw), p(poses), p(K), p(rays), p(self.d),
+                                            p(self.warped), B, V + 1, D, h, w, (V + 1) * 16, 9,
+                                            3 * h * w, st))
+            _lib.check(lib.dpv_head(p(self.bv), p(bv_resi), p(self.d), p(self.bv_upd), None, None,
+                                    None, None, None, B, D, h, w, ops.IN_LOGITS, st))
+        if head_hook is not None:
+            head_hook(0)
+        _lib.check(lib.dpv_head(p(logits_full), None, p(self.d), p(self.refined), None, p(self.depth),
+                                p(self.var), p(self.argmax), p(self.quarter), B, D, H, W,
+                                ops.IN_LOGITS, st))
+        if head_hook is not None:
+            head_hook(1)
+        rf, ri, cf, ci = self.luts
+        _lib.check(lib.dpv_ufield(p(self.refined), p(self.depth), p(self.d), p(intr_up), None,
+                                  p(rf), p(ri), p(cf), p(ci), p(self.uf), p(self.dz), p(self.ws),
+                                  B, D, H, W, 9, ops.IN_LOGPROB, *self.uf_params, self.pad_depth, st))
+
+    def launches_per_step(self):
+        return {"default": 5, "upsample": 6, "feedback": 7}[self.mode]
+
+    # -- algorithmic bytes, per step ---------------------------------
+    def algorithmic_bytes(self):
+        B, V, C, D = self.B, self.V, self.C, self.D
+        hw, HW = self.h * self.w, self.H * self.W
+        k = {
+            "sweep": 4 * hw * (C * (1 + V) + D) + 12 * hw,
+            "head_quarter": 8 * hw * D,
+            "head_full": 8 * HW * D + 16 * HW,
+            "ufield": 4 * HW * D + 4 * D * self.W + 8 * HW,
+        }
+        if self.mode == "upsample":
+            k["bayes_fuse"] = 12 * hw * D + 8 * hw
+        if self.mode == "feedback":
+            k["warp_feature"] = 8 * hw * D * (V + 1) + 12 * hw
+            k["feedback_fuse"] = 12 * hw * D
+        return {n: v * B for n, v in k.items()}

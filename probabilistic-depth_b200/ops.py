@@ -1,0 +1,349 @@
+"""Tensor-level entry points over the C ABI (include/dpv_b200.h).
+
+PyTorch is used for device memory and streams only: every function checks its
+arguments, allocates the outputs, and enqueues one (or two) of our kernels on
+the current torch stream through ctypes.  Nothing here computes on the CPU and
+nothing falls back to ATen ops; a missing library or a non-CUDA tensor raises.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+DIST = {"L2": 0, "L1": 1}
+IN_LOGITS, IN_LOGPROB, IN_PROB = 0, 1, 2
+_MODE = {"logits": IN_LOGITS, "logprob": IN_LOGPROB, "prob": IN_PROB}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _need(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise _lib.DpvError("%s must live on a CUDA device: the DPV kernels have no CPU path" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def _inner_contiguous(t, n_inner):
+    """True when the last n_inner dims are laid out contiguously."""
+    stride = 1
+    for size, st in zip(reversed(t.shape[-n_inner:]), reversed(t.stride()[-n_inner:])):
+        if size != 1 and st != stride:
+            return False
+        stride *= size
+    return True
+
+
+def _per_item(t, B, shape, name):
+    """Per-item constant given as [B,*shape] or broadcast as [*shape] / [1,*shape]."""
+    t = t.reshape((-1,) + tuple(shape)).contiguous()
+    if t.shape[0] == 1:
+        return t, 0
+    if t.shape[0] != B:
+        raise ValueError("%s must have 1 or %d items, got %d" % (name, B, t.shape[0]))
+    return t, int(np.prod(shape))
+
+
+_dcache = {}
+_dsum = {}
+
+
+def _bin_sum(d):
+    """sum_k d_k in fp32: E[d] of an all-zero log-DPV column (exp(0) = 1 per bin)."""
+    key = (d.data_ptr(), d.numel(), str(d.device))
+    v = _dsum.get(key)
+    if v is None:
+        v = float(np.sum(d.detach().cpu().numpy(), dtype=np.float32))   # once per bin set
+        _dsum[key] = v
+    return v
+
+
+def depth_bins(d_candi, device):
+    """fp32 device copy of the depth bins (the reference re-uploads them every call,
+    warping/homography.py:115); cached per content and device."""
+    if isinstance(d_candi, torch.Tensor):
+        return _need(d_candi, "d_candi").contiguous()
+    arr = np.ascontiguousarray(np.asarray(d_candi, dtype=np.float64))
+    key = (arr.tobytes(), str(device))
+    t = _dcache.get(key)
+    if t is None:
+        t = torch.from_numpy(arr.astype(np.float32)).to(device)
+        _dcache[key] = t
+        _dsum[(t.data_ptr(), t.numel(), str(t.device))] = float(np.sum(arr.astype(np.float32), dtype=np.float32))
+    return t
+
+
+# ----------------------------------------------------------------------------- K1 + K2a
+def sweep_cost_volume(ref, src, poses, K, rays, d_candi, sigma, dist="L2", algo=0,
+                      log_softmax=False):
+    """Plane-sweep cost volume, batched (reference warping/homography.py:98-135).
+
+    ref [B,C,H,W]; src [B,V,C,H,W]; poses [B,V,4,4] ([R|t] of each source view);
+    K [B,3,3] or [3,3]; rays [B,3,H*W] or [3,H*W].  The batch (and view) dimension
+    may be strided views of larger tensors; the inner [C,H,W] must be contiguous.
+    Returns cost [B,D,H,W] (and log_softmax(cost) when log_softmax=True).
+    """
+    _need(ref, "ref"), _need(src, "src"), _need(poses, "poses"), _need(K, "K"), _need(rays, "rays")
+    B, C, H, W = ref.shape
+    V = src.shape[1]
+    if src.shape != (B, V, C, H, W):
+        raise ValueError("src must be [B,V,C,H,W] matching ref")
+    if not _inner_contiguous(ref, 3):
+        ref = ref.contiguous()
+    if not _inner_contiguous(src, 3):
+        src = src.contiguous()
+    if poses.shape != (B, V, 4, 4):
+        raise ValueError("poses must be [B,V,4,4]")
+    if not _inner_contiguous(poses, 2) or (V > 1 and poses.stride(1) != 16):
+        poses = poses.contiguous()
+    K, k_bs = _per_item(K, B, (3, 3), "K")
+    rays, r_bs = _per_item(rays, B, (3, H * W), "rays")
+    d = depth_bins(d_candi, ref.device)
+    D = d.numel()
+    cost = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
+    lsm = torch.empty_like(cost) if log_softmax else None
+    lib = _lib.load()
+    _lib.check(lib.dpv_sweep_cost_volume(
+        _p(ref), _p(src), _p(poses), _p(K), _p(rays), _p(d), _p(cost), _p(lsm),
+        B, V, C, D, H, W,
+        ref.stride(0) if B > 1 else 0, src.stride(0) if B > 1 else 0, src.stride(1) if V > 1 else 0,
+        poses.stride(0) if B > 1 else 0, k_bs, r_bs,
+        float(sigma), DIST[dist], int(algo), _stream()))
+    return (cost, lsm) if log_softmax else cost
+
+
+def warp_planes(img, d, term1, term2, cx, cy, H, W):
+    """Per-plane bilinear warp (reference warping/homography.py:170-198).
+
+    img [N,C,H,W] (or [1,C,H,W] broadcast over the planes); d [N]; term1 [3,1];
+    term2 [3,H*W] -> [N,C,H,W].
+    """
+    _need(img, "img"), _need(d, "d"), _need(term1, "term1"), _need(term2, "term2")
+    N = d.numel()
+    C = img.shape[1]
+    if img.shape[0] not in (1, N) or img.shape[2:] != (H, W):
+        raise ValueError("img must be [N or 1, C, H, W]")
+    if not _inner_contiguous(img, 3):
+        img = img.contiguous()
+    nstride = 0 if img.shape[0] == 1 else img.stride(0)
+    term1 = term1.contiguous()
+    term2 = term2.contiguous()
+    out = torch.empty((N, C, H, W), device=img.device, dtype=torch.float32)
+    _lib.check(_lib.load().dpv_warp_planes(_p(img), _p(d.contiguous()), _p(term1), _p(term2), _p(out),
+                                           N, C, H, W, nstride, float(cx), float(cy), _stream()))
+    return out
+
+
+def warp_feature(feat, poses, K, rays, d_candi):
+    """Diagonal feature warp (reference warping/homography.py:137-168), batched.
+
+    feat [B,V,D,H,W]; poses [B,V,4,4] -> [B,V,D,H,W].
+    """
+    _need(feat, "feat"), _need(poses, "poses"), _need(K, "K"), _need(rays, "rays")
+    B, V, D, H, W = feat.shape
+    d = depth_bins(d_candi, feat.device)
+    if d.numel() != D:
+        raise ValueError("warp_feature needs as many channels as depth planes (%d vs %d)" % (D, d.numel()))
+    feat = feat.contiguous()
+    poses = poses.contiguous()
+    K, k_bs = _per_item(K, B, (3, 3), "K")
+    rays, r_bs = _per_item(rays, B, (3, H * W), "rays")
+    out = torch.empty_like(feat)
+    _lib.check(_lib.load().dpv_warp_feature(_p(feat), _p(poses), _p(K), _p(rays), _p(d), _p(out),
+                                            B, V, D, H, W, V * 16, k_bs, r_bs, _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- K3 / K4b
+def head(x, d_candi, addend=None, mode="logits", logp=True, prob=False, depth=False,
+         variance=False, argmax=False, quarter=False):
+    """Depth-bin head over x [B,D,H,W]; returns a dict with the requested outputs."""
+    _need(x, "x")
+    if x.dim() != 4:
+        raise ValueError("x must be [B,D,H,W]")
+    x = x.contiguous()
+    B, D, H, W = x.shape
+    if addend is not None:
+        _need(addend, "addend")
+        if addend.shape != x.shape:
+            raise ValueError("addend must match x")
+        addend = addend.contiguous()
+    d = depth_bins(d_candi, x.device)
+    if d.numel() != D:
+        raise ValueError("d_candi has %d bins, x has %d" % (d.numel(), D))
+    dev = x.device
+    out = {}
+    if logp:
+        out["logp"] = torch.empty_like(x)
+    if prob:
+        out["prob"] = torch.empty_like(x)
+    if depth:
+        out["depth"] = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+    if variance:
+        out["variance"] = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+    if argmax:
+        out["argmax"] = torch.empty((B, H, W), device=dev, dtype=torch.int64)
+    if quarter:
+        out["quarter"] = torch.empty((B, D, H // 4, W // 4), device=dev, dtype=torch.float32)
+    _lib.check(_lib.load().dpv_head(
+        _p(x), _p(addend), _p(d), _p(out.get("logp")), _p(out.get("prob")), _p(out.get("depth")),
+        _p(out.get("variance")), _p(out.get("argmax")), _p(out.get("quarter")),
+        B, D, H, W, _MODE[mode], _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- K4c
+def two_sigma_sq(var):
+    """2 * pow(sqrt(var), 2) in fp32, as utils/img_utils.py:24-25,40 evaluates it."""
+    s = np.sqrt(np.float32(var)).astype(np.float32)
+    return float(np.float32(2.0) * (s * s).astype(np.float32))
+
+
+def lidar_prior(dmaps, masks, d_candi, var=0.3):
+    """Prior DPV from sparse depth (reference utils/img_utils.py:360-375).
+    dmaps [B,H,W]; masks [B,1,H,W] -> [B,D,H,W]."""
+    _need(dmaps, "dmaps"), _need(masks, "masks")
+    B, H, W = dmaps.shape
+    d = depth_bins(d_candi, dmaps.device)
+    D = d.numel()
+    dmaps = dmaps.contiguous()
+    masks = masks.reshape(B, H, W).contiguous()
+    prior = torch.empty((B, D, H, W), device=dmaps.device, dtype=torch.float32)
+    _lib.check(_lib.load().dpv_lidar_prior(_p(dmaps), _p(masks), _p(d), _p(prior), B, D, H, W,
+                                           two_sigma_sq(var), _stream()))
+    return prior
+
+
+def bayes_fuse(bv, d_candi, prior=None, dmaps=None, masks=None, var=0.3, want_fused=True,
+               want_log=True):
+    """Multiply-and-renormalise fusion (reference models/models.py:669-672).
+    Either `prior` [B,D,H,W] or (`dmaps`, `masks`) must be given.  Returns (fused, log_fused)."""
+    _need(bv, "bv")
+    bv = bv.contiguous()
+    B, D, H, W = bv.shape
+    d = depth_bins(d_candi, bv.device)
+    if prior is not None:
+        prior = _need(prior, "prior").contiguous()
+    else:
+        dmaps = _need(dmaps, "dmaps").contiguous()
+        masks = _need(masks, "masks").reshape(B, H, W).contiguous()
+    fused = torch.empty_like(bv) if want_fused else None
+    logf = torch.empty_like(bv) if want_log else None
+    _lib.check(_lib.load().dpv_bayes_fuse(_p(bv), _p(prior), _p(dmaps), _p(masks), _p(d), _p(fused),
+                                          _p(logf), B, D, H, W, two_sigma_sq(var), _stream()))
+    return fused, logf
+
+
+# ----------------------------------------------------------------------------- K5
+_lut_cache = {}
+
+
+def shift_luts(H, W, pshift, device):
+    """Index maps of the reference's +/-pshift nearest-neighbour shifts.
+
+    utils/img_utils.py:170-176,291-302,336 build a normalised grid with step
+    2/(size-1) and sample it with grid_sample(nearest, align_corners=False); the
+    resulting source indices differ from `y - pshift` at the borders (half-pixel
+    ties).  Rather than re-deriving that rounding, run the same grid construction
+    once per shape on an index image (host side, cached) and keep the integer maps.
+    Returns int32 device tensors (row_fwd [H], row_inv [H], col_fwd [W], col_inv [W]),
+    -1 meaning "samples the zero padding".
+    """
+    key = (H, W, int(pshift), str(device))
+    hit = _lut_cache.get(key)
+    if hit is not None:
+        return hit
+    if pshift == 0:
+        rows = torch.arange(H, dtype=torch.int32)
+        cols = torch.arange(W, dtype=torch.int32)
+        luts = (rows, rows.clone(), cols, cols.clone())
+    else:
+        import torch.nn.functional as F
+        yv, xv = torch.meshgrid([torch.arange(0, H).float(), torch.arange(0, W).float()], indexing="ij")
+        ystep, xstep = 2.0 / float(H - 1), 2.0 / float(W - 1)
+        index_img = (torch.arange(H * W, dtype=torch.float32) + 1.0).reshape(1, 1, H, W)
+        luts = []
+        maps = []
+        for s in (float(pshift), -float(pshift)):
+            g = torch.zeros((1, H, W, 2), dtype=torch.float32)
+            g[:, :, :, 1] = s
+            g[0, :, :, 0] = -1 + xv * xstep - g[0, :, :, 0] * xstep
+            g[0, :, :, 1] = -1 + yv * ystep - g[0, :, :, 1] * ystep
+            m = F.grid_sample(index_img, g, mode="nearest", align_corners=False)[0, 0].long() - 1
+            maps.append(m)
+        rl, cl = [], []
+        for m in maps:
+            valid = m >= 0
+            sy = torch.where(valid, m // W, torch.full_like(m, -1)).max(dim=1).values
+            sx = torch.where(valid, m % W, torch.full_like(m, -1)).max(dim=0).values
+            rebuilt = torch.where((sy[:, None] >= 0) & (sx[None, :] >= 0), sy[:, None] * W + sx[None, :],
+                                  torch.full_like(m, -1))
+            if not torch.equal(rebuilt, m):
+                raise _lib.DpvError("shift map is not separable; cannot build row/column tables")
+            rl.append(sy.int())
+            cl.append(sx.int())
+        luts = (rl[0], rl[1], cl[0], cl[1])
+    luts = tuple(t.contiguous().to(device) for t in luts)
+    _lut_cache[key] = luts
+    return luts
+
+
+KITTI_UF = dict(pshift=5, zstart=0.6, zend=0.6 + 0.3, maxd=100.0, mind=0.0)
+
+
+def ufield(dpv, d_candi, intr_up, mode="logprob", mask=None, depth=None, params=None):
+    """Uncertainty-field collapse, batched (reference utils/img_utils.py:268-358).
+
+    dpv [B,D,H,W] in `mode` ("logprob" or "prob"); intr_up [B,3,3] or [3,3]; mask
+    [B,H,W] optional; depth [B,H,W] optional precomputed E[d].
+    Returns (uf [B,D,W], depth_zero [B,H,W]).
+    """
+    _need(dpv, "dpv")
+    dpv = dpv.contiguous()
+    B, D, H, W = dpv.shape
+    p = dict(KITTI_UF if params is None else params)
+    d = depth_bins(d_candi, dpv.device)
+    if depth is None:
+        depth = head(dpv, d, mode=mode, logp=False, depth=True)["depth"]
+    depth = _need(depth, "depth").contiguous()
+    intr_up, i_bs = _per_item(_need(intr_up, "intr_up"), B, (3, 3), "intr_up")
+    if mask is not None:
+        mask = _need(mask, "mask").reshape(B, H, W).contiguous()
+    rf, ri, cf, ci = shift_luts(H, W, p["pshift"], dpv.device)
+    lib = _lib.load()
+    ws = torch.empty((int(lib.dpv_ufield_workspace_floats(B, D, H, W)),), device=dpv.device,
+                     dtype=torch.float32)
+    uf = torch.empty((B, D, W), device=dpv.device, dtype=torch.float32)
+    dz = torch.empty((B, H, W), device=dpv.device, dtype=torch.float32)
+    pad_depth = _bin_sum(d) if mode == "logprob" else 0.0
+    f32 = lambda v: float(np.float32(v))
+    _lib.check(lib.dpv_ufield(_p(dpv), _p(depth), _p(d), _p(intr_up), _p(mask), _p(rf), _p(ri),
+                              _p(cf), _p(ci), _p(uf), _p(dz), _p(ws), B, D, H, W, i_bs, _MODE[mode],
+                              f32(p["zstart"]), f32(p["zend"]), f32(p["maxd"]), f32(p["mind"]),
+                              pad_depth, _stream()))
+    return uf, dz
+
+
+# ----------------------------------------------------------------------------- K2b
+def correlation(x1, x2, max_displacement=4):
+    """Local correlation [B,(2r+1)^2,H,W] (reference models/correlation_native.py:13-23)."""
+    _need(x1, "x1"), _need(x2, "x2")
+    if x1.shape != x2.shape or x1.dim() != 4:
+        raise ValueError("x1, x2 must be [B,C,H,W] of equal shape")
+    x1 = x1.contiguous()
+    x2 = x2.contiguous()
+    B, C, H, W = x1.shape
+    n = 2 * int(max_displacement) + 1
+    out = torch.empty((B, n * n, H, W), device=x1.device, dtype=torch.float32)
+    _lib.check(_lib.load().dpv_correlation(_p(x1), _p(x2), _p(out), B, C, H, W,
+                                           int(max_displacement), _stream()))
+    return out

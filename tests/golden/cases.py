@@ -1,0 +1,147 @@
+"""Seeded input builders shared by make_golden.py (reference side) and the tests.
+
+Every case is a function seed -> dict of numpy arrays, so the golden files only
+need to hold the reference OUTPUTS; inputs are regenerated bit-identically from
+the legacy numpy RandomState streams.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+synth = importlib.import_module("probabilistic-depth_b200.synth")
+
+D_CANDI = synth.depth_candidates(5.0, 40.0, 64, 1.0)
+
+
+def _cam(w, h):
+    return synth.intrinsics(w, h), synth.unit_rays(w, h)
+
+
+def sweep_case(name):
+    """Inputs for est_swp_volume_v4.  Returns dict(ref, src, R, t, K, rays, d_candi, sigma)."""
+    spec = {
+        # name:            (h,  w,  C,  V, D,  pose kind,             seed)
+        "mono_small":      (16, 24, 67, 1, 64, "mono", 11),
+        "mono_yaw_2view":  (20, 28, 19, 2, 32, "mono2", 12),
+        "stereo_small":    (16, 24, 67, 1, 64, "stereo", 13),
+        "oob_heavy":       (12, 20, 8, 1, 16, "oob", 14),
+        "mono_ref_shape":  (64, 96, 67, 1, 64, "mono", 15),
+        "stereo_ref_shape": (64, 96, 67, 1, 64, "stereo", 16),
+        "odd_dims":        (13, 17, 5, 1, 7, "mono", 17),
+    }[name]
+    h, w, C, V, D, kind, seed = spec
+    K, rays = _cam(w, h)
+    d = synth.depth_candidates(5.0, 40.0, D, 1.0)
+    ref = synth.randn(seed, 1, C, h, w)
+    src = synth.randn(seed + 1000, 1, V, C, h, w)
+    if kind == "mono":
+        poses = [synth.pose(synth.yaw_matrix(0.7), (0.05, -0.02, 0.8))]
+    elif kind == "mono2":
+        poses = [synth.pose(synth.yaw_matrix(0.7), (0.05, -0.02, 0.8)),
+                 synth.pose(synth.yaw_matrix(-1.0), (-0.1, 0.03, -0.6))]
+    elif kind == "stereo":
+        poses = [synth.pose(None, (-0.54, 0.0, 0.0))]
+    elif kind == "oob":
+        poses = [synth.pose(synth.yaw_matrix(12.0), (1.5, 0.4, 0.5))]
+    P = np.stack(poses)
+    return dict(ref=ref, src=src, R=np.ascontiguousarray(P[:, :3, :3]),
+                t=np.ascontiguousarray(P[:, :3, 3]), K=K, rays=rays, d_candi=d,
+                sigma=10.0, h=h, w=w)
+
+
+SWEEP_CASES = ["mono_small", "mono_yaw_2view", "stereo_small", "oob_heavy",
+               "mono_ref_shape", "stereo_ref_shape", "odd_dims"]
+
+
+def warp_feature_case(name):
+    spec = {
+        "small":     (16, 24, 16, 21),
+        "ref_shape": (64, 96, 64, 22),
+    }[name]
+    h, w, D, seed = spec
+    K, rays = _cam(w, h)
+    d = synth.depth_candidates(5.0, 40.0, D, 1.0)
+    feat = synth.randn(seed, 1, 2, D, h, w)
+    P = np.stack([synth.pose(synth.yaw_matrix(0.7), (0.05, -0.02, 0.8)), synth.pose()])
+    return dict(feat=feat, R=np.ascontiguousarray(P[:, :3, :3]),
+                t=np.ascontiguousarray(P[:, :3, 3]), K=K, rays=rays, d_candi=d, h=h, w=w)
+
+
+WARP_FEATURE_CASES = ["small", "ref_shape"]
+
+
+def softmax_case(name):
+    spec = {
+        "small":    (2, 64, 16, 24, 31, 3.0),
+        "wide":     (1, 64, 32, 48, 32, 12.0),
+        "d32":      (3, 32, 9, 13, 33, 2.0),
+        "d128":     (1, 128, 8, 12, 34, 5.0),
+    }[name]
+    B, D, h, w, seed, scale = spec
+    x = synth.randn(seed, B, D, h, w) * np.float32(scale)
+    if name == "wide":
+        # exact ties and near-ties for the arg-max rule (first maximum wins)
+        x[0, 5, 0, :] = x[0, 9, 0, :] = np.float32(40.0)
+        x[0, 7, 1, :] = np.float32(41.0)
+        x[0, 3, 1, :] = np.nextafter(np.float32(41.0), np.float32(0.0))
+        x[0, :, 2, :] = np.float32(1.25)
+    d = synth.depth_candidates(5.0, 40.0, D, 1.0)
+    return dict(x=x, d_candi=d)
+
+
+SOFTMAX_CASES = ["small", "wide", "d32", "d128"]
+
+
+def fuse_case(name):
+    spec = {"small": (2, 64, 16, 24, 41), "ref_shape": (1, 64, 64, 96, 42)}[name]
+    B, D, h, w, seed = spec
+    d = synth.depth_candidates(5.0, 40.0, D, 1.0)
+    bv_logits = synth.randn(seed, B, D, h, w) * np.float32(2.0)
+    resi = synth.randn(seed + 1, B, D, h, w)
+    dm, mask = synth.sparse_depth(seed + 2, B, h, w, keep=0.3)
+    # a few depths outside the bin range (NaN -> -1 -> clamp branch, img_utils.py:45)
+    dm[0, 0, :4] = np.float32([0.0, 400.0, 4.9, 41.0])
+    mask[0, 0, 0, :4] = 1.0
+    return dict(bv_logits=bv_logits, resi=resi, dmaps=dm, masks=mask, d_candi=d)
+
+
+FUSE_CASES = ["small", "ref_shape"]
+
+
+def ufield_case(name):
+    spec = {
+        # name          (H,   W,   seed, with_mask, log)
+        "small_log":    (64, 96, 51, False, True),
+        "full_log":     (256, 384, 52, False, True),
+        "full_mask_lin": (256, 384, 53, True, False),
+        "odd_log":      (37, 51, 54, False, True),
+    }[name]
+    H, W, seed, with_mask, log = spec
+    K = synth.intrinsics(W // 4 if W % 4 == 0 else W, H // 4 if H % 4 == 0 else H)
+    Ku = synth.intrinsics_up(K) if (W % 4 == 0 and H % 4 == 0) else K
+    logits = synth.ground_plane_logits(seed, 1, H, W, D_CANDI, Ku)
+    mask = None
+    if with_mask:
+        mask = (synth.rng(seed + 1).uniform(size=(1, H, W)) < 0.7).astype(np.float32)
+    return dict(logits=logits, d_candi=D_CANDI, intr_up=Ku, mask=mask, log=log)
+
+
+UFIELD_CASES = ["small_log", "full_log", "full_mask_lin", "odd_log"]
+
+
+def corr_case(name):
+    spec = {
+        "tiny":   (2, 8, 6, 13, 61),
+        "lvl":    (2, 32, 24, 52, 62),
+        "c96":    (1, 96, 12, 26, 63),
+    }[name]
+    B, C, H, W, seed = spec
+    return dict(x1=synth.randn(seed, B, C, H, W), x2=synth.randn(seed + 1, B, C, H, W))
+
+
+CORR_CASES = ["tiny", "lvl", "c96"]

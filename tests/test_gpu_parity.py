@@ -1,0 +1,331 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures produced by the reference itself.
+
+Tolerances (BASELINE.json north_star: "argmax depth-bin indices bit-exact, and DPV, expected
+depth and variance within 1e-4 relative in fp32"):
+  cost volume / warps       rtol 1e-4 (+ atol 1e-5 for values near zero)
+  log-DPV                   |y - y_ref| <= 1e-4 * max(1, |y_ref|)
+  E[d], Var[d]              rtol 1e-4 (Var oracle is float64)
+  argmax                    exact
+  UF                        same NaN pattern, rtol 1e-4 on columns without a pixel within 1e-4 of a
+                            mask threshold (a flipped pixel changes a column discretely)
+  correlation               atol 2e-7 (the reference's own bar is atol 1e-7 between its CUDA and
+                            torch versions, models/correlation_native.py:64; summation order differs)
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import dpv_oracle as O
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+def cu(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def close(a, b, rtol=1e-4, atol=1e-5):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+
+
+def logclose(a, b, tol=1e-4):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    assert err.max() <= tol, "max scaled error %g" % err.max()
+
+
+def cam_dict(c):
+    return {"intrinsic_M_cuda": cu(c["K"]), "intrinsic_M": c["K"], "unit_ray_array_2D": cu(c["rays"])}
+
+
+# ------------------------------------------------------------------------- K1 + K2a
+@pytest.mark.parametrize("name", cases.SWEEP_CASES)
+@pytest.mark.parametrize("dist,algo", [("L2", 2), ("L2", 1), ("L1", 1)])
+def test_sweep_vs_golden(dpv, golden, name, dist, algo):
+    g = golden("sweep")
+    key = "%s_%s" % (name, dist)
+    c = cases.sweep_case(name)
+    if key in g.files:
+        want = g[key]
+    else:
+        want = O.plane_sweep_cost(T(c["ref"]), T(c["src"]), c["d_candi"], T(c["R"]), T(c["t"]),
+                                  T(c["K"]), T(c["rays"]), c["sigma"], dist).numpy()
+    V = c["src"].shape[1]
+    poses = np.zeros((1, V, 4, 4), np.float32)
+    poses[0, :, :3, :3] = c["R"]
+    poses[0, :, :3, 3] = c["t"]
+    poses[0, :, 3, 3] = 1
+    got = dpv.ops.sweep_cost_volume(cu(c["ref"]), cu(c["src"]), cu(poses), cu(c["K"]), cu(c["rays"]),
+                                    c["d_candi"], c["sigma"], dist=dist, algo=algo)
+    close(got, want)
+
+
+@pytest.mark.parametrize("name", ["mono_small", "mono_yaw_2view", "oob_heavy"])
+def test_est_swp_volume_v4_mirror(dpv, golden, name):
+    """Through the reference-shaped function (warping/homography.py:98)."""
+    c = cases.sweep_case(name)
+    got = dpv.warping.homography.est_swp_volume_v4(cu(c["ref"]), cu(c["src"]), c["d_candi"],
+                                                   cu(c["R"]), cu(c["t"]), cam_dict(c), c["sigma"],
+                                                   feat_dist="L2")
+    close(got, golden("sweep")[name + "_L2"])
+    with pytest.raises(Exception, match="undefined metric"):
+        dpv.warping.homography.est_swp_volume_v4(cu(c["ref"]), cu(c["src"]), c["d_candi"], cu(c["R"]),
+                                                 cu(c["t"]), cam_dict(c), c["sigma"], feat_dist="L3")
+
+
+def test_sweep_batched_strided_and_fused_softmax(dpv):
+    """One launch over B items laid out as the model holds them ([B, 2, C, h, w], reference view
+    last, models/models.py:519-535), per-item poses, against the per-item oracle."""
+    B, C, h, w, D = 3, 67, 16, 24, 64
+    synth = dpv.synth
+    d = synth.depth_candidates(5, 40, D)
+    feats = synth.randn(71, B, 2, C, h, w)
+    poses = np.stack([
+        np.stack([synth.pose(synth.yaw_matrix(0.7), (0.05, -0.02, 0.8)), synth.pose()]),
+        np.stack([synth.pose(None, (-0.54, 0, 0)), synth.pose()]),
+        np.stack([synth.pose(synth.yaw_matrix(-2.0), (0.3, 0.1, -0.4)), synth.pose()])]).astype(np.float32)
+    cam = synth.camera(w, h, B)
+    f = cu(feats)
+    p = cu(poses)
+    cost, lsm = dpv.ops.sweep_cost_volume(f[:, -1], f[:, :-1], p[:, :-1], cu(cam["intrinsics"]),
+                                          cu(cam["unit_ray"]), d, 10.0, log_softmax=True)
+    for b in range(B):
+        want = O.plane_sweep_cost(T(feats[b:b + 1, -1]), T(feats[b:b + 1, :-1]), d,
+                                  T(poses[b, :-1, :3, :3]), T(poses[b, :-1, :3, 3]),
+                                  T(cam["intrinsics"][b]), T(cam["unit_ray"][b]), 10.0, "L2")
+        close(cost[b:b + 1], want.numpy())
+        logclose(lsm[b:b + 1], O.log_softmax_bins(want).numpy())
+
+
+def test_sweep_identity_pose_is_near_zero(dpv):
+    """Size-independent property at the model's shape: source == reference under the identity
+    pose gives a cost volume that is ~0 (only coordinate rounding, SURVEY.md 7 'bit-level')."""
+    C, h, w, D = 67, 64, 96, 64
+    synth = dpv.synth
+    ref = synth.randn(5, 1, C, h, w)
+    poses = synth.pose()[None, None]
+    cam = synth.camera(w, h, 1)
+    for algo in (1, 2):
+        cost = dpv.ops.sweep_cost_volume(cu(ref), cu(ref[:, None]), cu(poses), cu(cam["intrinsics"]),
+                                         cu(cam["unit_ray"]), synth.depth_candidates(5, 40, D), 10.0,
+                                         algo=algo)
+        assert float(cost.abs().max()) < 1e-5 * C
+
+
+# ------------------------------------------------------------------------- K1 alone, K4a
+def test_warp_planes_vs_oracle(dpv):
+    c = cases.sweep_case("mono_small")
+    K, R, t, rays = T(c["K"]), T(c["R"][0]), T(c["t"][0]), T(c["rays"])
+    term1, term2 = O.sweep_terms(K, R, t, rays)
+    d = torch.from_numpy(c["d_candi"].astype(np.float32))
+    cx, cy = np.float32(c["K"][0, 2]), np.float32(c["K"][1, 2])
+    want = O.back_warp_planes(T(c["src"][0, 0]), d, term1, term2, cx, cy, c["h"], c["w"])
+    src = cu(c["src"][0, 0])
+    stack = src.unsqueeze(0).repeat(d.numel(), 1, 1, 1)
+    got = dpv.warping.homography._back_warp_homo_parallel(
+        stack, d.cuda(), term1.cuda(), term2.cuda(), {"intrinsic_M": c["K"]}, c["h"], c["w"])
+    close(got, want.numpy(), rtol=1e-4, atol=2e-5)
+    got2 = dpv.ops.warp_planes(src.unsqueeze(0), d.cuda(), term1.cuda(), term2.cuda(), cx, cy,
+                               c["h"], c["w"])
+    assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("name", cases.WARP_FEATURE_CASES)
+def test_warp_feature(dpv, golden, name):
+    c = cases.warp_feature_case(name)
+    got = dpv.warping.homography.warp_feature(cu(c["feat"]), c["d_candi"], cu(c["R"]), cu(c["t"]),
+                                              cam_dict(c))
+    got = got if name == "small" else got[:, :, ::4]
+    close(got, golden("warp_feature")[name], rtol=1e-4, atol=2e-5)
+    with pytest.raises(Exception, match="Warped Accum Error"):
+        dpv.warping.homography.warp_feature(cu(np.concatenate([c["feat"]] * 2)), c["d_candi"],
+                                            cu(c["R"]), cu(c["t"]), cam_dict(c))
+
+
+# ------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("name", cases.SOFTMAX_CASES)
+def test_head_vs_golden(dpv, golden, name):
+    g = golden("softmax")
+    c = cases.softmax_case(name)
+    x = cu(c["x"])
+    out = dpv.ops.head(x, c["d_candi"], logp=True, prob=True, depth=True, variance=True, argmax=True,
+                       quarter=(name + "_quarter") in g.files)
+    logclose(out["logp"], g[name + "_logdpv"])
+    close(out["prob"], np.exp(g[name + "_logdpv"]), rtol=1e-4, atol=1e-9)
+    close(out["depth"], g[name + "_depth"], rtol=1e-4, atol=0)
+    close(out["variance"], g[name + "_var"].astype(np.float32), rtol=1e-4, atol=1e-6)
+    np.testing.assert_array_equal(out["argmax"].cpu().numpy(), g[name + "_argmax"])
+    if "quarter" in out:
+        logclose(out["quarter"], g[name + "_quarter"])
+        assert torch.equal(out["quarter"], out["logp"][:, :, ::4, ::4])
+
+
+def test_head_modes_and_mirrors(dpv, golden):
+    """dpv_to_depthmap on log / linear DPVs (utils/img_utils.py:52-61) and its B != 1 error."""
+    g = golden("softmax")
+    c = cases.softmax_case("wide")
+    logdpv = cu(g["wide_logdpv"])
+    iu = dpv.utils.img_utils
+    close(iu.dpv_to_depthmap(logdpv, c["d_candi"], BV_log=True), g["wide_depth"], rtol=1e-4, atol=0)
+    close(iu.dpv_to_depthmap(torch.exp(logdpv), c["d_candi"], BV_log=False), g["wide_depth"],
+          rtol=1e-4, atol=0)
+    close(iu.depth_variance(logdpv, c["d_candi"]), g["wide_var"].astype(np.float32), rtol=1e-4, atol=1e-6)
+    with pytest.raises(Exception, match="Unable to handle this case"):
+        iu.dpv_to_depthmap(torch.cat([logdpv, logdpv]), c["d_candi"], BV_log=True)
+
+
+def test_head_full_size_properties(dpv):
+    """BASELINE size (B=8, D=64, 256x384): invariants that need no oracle."""
+    B, D, H, W = 8, 64, 256, 384
+    d = dpv.synth.depth_candidates(5, 40, D)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((B, D, H, W), device="cuda", generator=gen) * 4.0
+    out = dpv.ops.head(x, d, logp=True, prob=True, depth=True, variance=True, argmax=True, quarter=True)
+    total = out["prob"].sum(1)
+    assert float((total - 1).abs().max()) < 1e-5
+    assert torch.equal(out["argmax"], torch.argmax(out["logp"], dim=1))
+    picked = torch.gather(out["logp"], 1, out["argmax"].unsqueeze(1)).squeeze(1)
+    assert torch.equal(picked, out["logp"].max(1).values)
+    assert float(out["depth"].min()) >= 5.0 - 1e-4 and float(out["depth"].max()) <= 40.0 + 1e-4
+    assert float(out["variance"].min()) >= 0.0
+    assert torch.equal(out["quarter"], out["logp"][:, :, ::4, ::4])
+    # idempotence: the head applied to its own log-DPV returns it unchanged (to rounding)
+    again = dpv.ops.head(out["logp"], d, logp=True)["logp"]
+    assert float((again - out["logp"]).abs().max()) < 2e-6
+    # shift invariance of soft-max
+    shifted = dpv.ops.head(x + 3.0, d, logp=True)["logp"]
+    assert float((shifted - out["logp"]).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------- K4b, K4c
+@pytest.mark.parametrize("name", cases.FUSE_CASES)
+def test_fusion(dpv, golden, name):
+    g = golden("fuse")
+    c = cases.fuse_case(name)
+    bv = dpv.ops.head(cu(c["bv_logits"]), c["d_candi"], logp=True)["logp"]
+    fused, logf = dpv.ops.bayes_fuse(bv, c["d_candi"], dmaps=cu(c["dmaps"]), masks=cu(c["masks"]), var=0.3)
+    logclose(logf, g[name + "_logfused"])
+    if name == "small":
+        prior = dpv.utils.img_utils.gen_dpv_withmask(cu(c["dmaps"]), cu(c["masks"]), c["d_candi"], 0.3)
+        close(prior, g[name + "_prior"], rtol=1e-4, atol=1e-12)
+        close(fused, g[name + "_fused"], rtol=1e-4, atol=1e-12)
+        fused2, logf2 = dpv.ops.bayes_fuse(bv, c["d_candi"], prior=prior)
+        assert torch.equal(fused2, fused) and torch.equal(logf2, logf)
+        upd = dpv.ops.head(bv, c["d_candi"], addend=cu(c["resi"]), logp=True)["logp"]
+        logclose(upd, g[name + "_feedback"])
+
+
+# ------------------------------------------------------------------------- K5
+def _near_threshold_columns(c, log):
+    """Columns holding a pixel whose height/depth is within 1e-4 (relative) of a mask threshold."""
+    ls = O.log_softmax_bins(T(c["logits"]))
+    dpvv = ls if log else torch.exp(ls)
+    H, W = dpvv.shape[2:]
+    g_fwd, _ = O._shift_grids(H, W, 5)
+    shifted = torch.nn.functional.grid_sample(dpvv, g_fwd, mode="nearest", align_corners=False)
+    z = O.expected_depth(shifted, c["d_candi"], log=log)
+    pts = O.depth_to_points(z, T(c["intr_up"]))
+    bad = torch.zeros((H, W), dtype=torch.bool)
+    for val, thr in ((pts[1], 0.9), (pts[1], 0.6), (pts[2], 99.0), (pts[2], 0.0)):
+        bad |= (val - thr).abs() <= 1e-4 * max(1.0, abs(thr))
+    cols = bad.any(0)
+    # the mask is shifted back up by 5 rows and keeps its column: same column index
+    return cols.numpy()
+
+
+@pytest.mark.parametrize("name", cases.UFIELD_CASES)
+def test_ufield(dpv, golden, name):
+    g = golden("ufield")
+    c = cases.ufield_case(name)
+    ls = dpv.ops.head(cu(c["logits"]), c["d_candi"], logp=True)["logp"]
+    vol = ls if c["log"] else torch.exp(ls)
+
+    class cfg:
+        class data:
+            dataset_path = "./kitti/"
+    uf, dz = dpv.utils.img_utils.gen_ufield(vol, c["d_candi"], cu(c["intr_up"]), BV_log=c["log"],
+                                            mask=cu(c["mask"]), cfg=cfg)
+    want_uf, want_dz = g[name + "_uf"], g[name + "_depthzero"]
+    keep = ~_near_threshold_columns(c, c["log"])
+    assert keep.mean() > 0.9
+    uf = uf.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(uf[:, :, keep]), np.isnan(want_uf[:, :, keep]))
+    np.testing.assert_allclose(uf[:, :, keep], want_uf[:, :, keep], rtol=1e-4, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(dz.cpu().numpy()[:, :, keep], want_dz[:, :, keep], rtol=1e-4, atol=0)
+
+
+# ------------------------------------------------------------------------- K2b
+@pytest.mark.parametrize("name", cases.CORR_CASES)
+def test_correlation(dpv, golden, name):
+    c = cases.corr_case(name)
+    want = golden("correlation")[name]
+    native = dpv.models.correlation_native.Correlation(max_displacement=4)
+    got = native(cu(c["x1"]), cu(c["x2"]))
+    close(got, want, rtol=0, atol=2e-7)
+    ext = dpv.models.correlation_package.correlation.Correlation(
+        pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
+    assert torch.equal(ext(cu(c["x1"]), cu(c["x2"])), got)
+    # generic-radius kernel against the oracle
+    got3 = dpv.ops.correlation(cu(c["x1"]), cu(c["x2"]), 2)
+    close(got3, O.local_correlation(T(c["x1"]), T(c["x2"]), 2).numpy(), rtol=0, atol=2e-7)
+
+
+def test_correlation_linearity_full_size(dpv):
+    """PWC-Lite's largest level (models/pwclite.py:177-186): corr is linear in its first input."""
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x1 = torch.randn((2, 32, 96, 208), device="cuda", generator=gen)
+    x1b = torch.randn((2, 32, 96, 208), device="cuda", generator=gen)
+    x2 = torch.randn((2, 32, 96, 208), device="cuda", generator=gen)
+    f = dpv.ops.correlation
+    lhs = f(2.0 * x1 + x1b, x2)
+    rhs = 2.0 * f(x1, x2) + f(x1b, x2)
+    assert float((lhs - rhs).abs().max()) < 5e-6
+
+
+# ------------------------------------------------------------------------- no CPU path
+def test_cpu_tensors_are_refused(dpv):
+    c = cases.softmax_case("small")
+    with pytest.raises(dpv.DpvError):
+        dpv.ops.head(T(c["x"]), c["d_candi"])
+
+
+# ------------------------------------------------------------------------- host pipeline
+def test_host_pipeline_matches_ops(dpv):
+    B, V, C, D, h, w, H, W = 2, 1, 67, 64, 16, 24, 64, 96
+    synth = dpv.synth
+    d = synth.depth_candidates(5, 40, D)
+    feats = synth.randn(81, B, V + 1, C, h, w)
+    poses = synth.stereo_poses(B)
+    cam = synth.camera(w, h, B)
+    logits = synth.ground_plane_logits(82, B, H, W, d, cam["intrinsics_up"][0])
+    from importlib import import_module
+    pl = import_module("probabilistic-depth_b200.pipeline")
+    pipe = pl.FramePipeline(B, V, C, D, h, w, H, W)
+    out = pipe.run(T(feats).pin_memory(), T(poses).pin_memory(), T(cam["intrinsics"]).pin_memory(),
+                   T(cam["unit_ray"]).pin_memory(), d, T(logits).pin_memory(),
+                   T(cam["intrinsics_up"]).pin_memory(), 10.0, pipe.outputs())
+    h2d, d2h = pipe.last_bytes()
+    assert h2d > feats.nbytes + logits.nbytes and d2h > 0
+    f, p = cu(feats), cu(poses)
+    cost = dpv.ops.sweep_cost_volume(f[:, -1], f[:, :-1], p[:, :-1], cu(cam["intrinsics"]),
+                                     cu(cam["unit_ray"]), d, 10.0)
+    bv = dpv.ops.head(cost, d, logp=True)["logp"]
+    hd = dpv.ops.head(cu(logits), d, logp=True, depth=True, variance=True, argmax=True, quarter=True)
+    uf, dz = dpv.ops.ufield(hd["logp"], d, cu(cam["intrinsics_up"]), depth=hd["depth"])
+    assert torch.equal(out["bv"], bv.cpu())
+    assert torch.equal(out["depth"], hd["depth"].cpu())
+    assert torch.equal(out["variance"], hd["variance"].cpu())
+    assert torch.equal(out["argmax"], hd["argmax"].cpu())
+    assert torch.equal(out["quarter"], hd["quarter"].cpu())
+    np.testing.assert_array_equal(out["uf"].numpy(), uf.cpu().numpy())
+    assert torch.equal(out["depth_zero"], dz.cpu())
+    pipe.close()

@@ -1,0 +1,98 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/*.npz).
+
+The reference has no tests or golden vectors of its own for this path
+(SURVEY.md section 4); the fixtures were produced by tests/golden/make_golden.py,
+which imports the unmodified reference.  The oracle calls the same ATen ops, so
+agreement is expected to be bit-exact or within a few ulp.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import dpv_oracle as O
+
+T = torch.from_numpy
+
+
+def _close(a, b, rtol=1e-6, atol=1e-6):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", cases.SWEEP_CASES)
+@pytest.mark.parametrize("dist", ["L2", "L1"])
+def test_sweep(golden, name, dist):
+    g = golden("sweep")
+    key = "%s_%s" % (name, dist)
+    if key not in g.files:
+        pytest.skip("no golden for this combination")
+    c = cases.sweep_case(name)
+    cv = O.plane_sweep_cost(T(c["ref"]), T(c["src"]), c["d_candi"], T(c["R"]), T(c["t"]),
+                            T(c["K"]), T(c["rays"]), c["sigma"], dist)
+    _close(cv.numpy(), g[key], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", cases.WARP_FEATURE_CASES)
+def test_warp_feature(golden, name):
+    c = cases.warp_feature_case(name)
+    wf = O.warp_feature_diag(T(c["feat"]), c["d_candi"], T(c["R"]), T(c["t"]), T(c["K"]),
+                             T(c["rays"])).numpy()
+    if name != "small":
+        wf = wf[:, :, ::4]
+    _close(wf, golden("warp_feature")[name])
+
+
+@pytest.mark.parametrize("name", cases.SOFTMAX_CASES)
+def test_softmax_moments(golden, name):
+    g = golden("softmax")
+    c = cases.softmax_case(name)
+    x = T(c["x"])
+    ls = O.log_softmax_bins(x)
+    np.testing.assert_array_equal(ls.numpy(), g[name + "_logdpv"])
+    for b in range(x.shape[0]):
+        np.testing.assert_array_equal(
+            O.expected_depth(ls[b:b + 1], c["d_candi"], log=True)[0].numpy(), g[name + "_depth"][b])
+        np.testing.assert_array_equal(O.depth_variance(ls[b], c["d_candi"]).numpy(),
+                                      g[name + "_var"][b])
+    np.testing.assert_array_equal(O.argmax_bin(ls).numpy(), g[name + "_argmax"])
+    if name + "_quarter" in g.files:
+        np.testing.assert_array_equal(O.quarter_nearest(ls).numpy(), g[name + "_quarter"])
+
+
+@pytest.mark.parametrize("name", cases.FUSE_CASES)
+def test_fusion(golden, name):
+    g = golden("fuse")
+    c = cases.fuse_case(name)
+    bv = O.log_softmax_bins(T(c["bv_logits"]))
+    prior = O.lidar_prior(T(c["dmaps"]), T(c["masks"]), c["d_candi"], 0.3)
+    fused, logf = O.bayes_fuse(bv, prior)
+    np.testing.assert_array_equal(logf.numpy(), g[name + "_logfused"])
+    if name == "small":
+        np.testing.assert_array_equal(prior.numpy(), g[name + "_prior"])
+        np.testing.assert_array_equal(fused.numpy(), g[name + "_fused"])
+        np.testing.assert_array_equal(O.feedback_fuse(bv, T(c["resi"])).numpy(),
+                                      g[name + "_feedback"])
+
+
+@pytest.mark.parametrize("name", cases.UFIELD_CASES)
+def test_ufield(golden, name):
+    g = golden("ufield")
+    c = cases.ufield_case(name)
+    ls = O.log_softmax_bins(T(c["logits"]))
+    dpv = ls if c["log"] else torch.exp(ls)
+    mask = None if c["mask"] is None else T(c["mask"])
+    uf, dz = O.uncertainty_field(dpv, c["d_candi"], T(c["intr_up"]), log=c["log"], mask=mask)
+    np.testing.assert_array_equal(np.isnan(uf.numpy()), np.isnan(g[name + "_uf"]))
+    np.testing.assert_array_equal(uf.numpy(), g[name + "_uf"])
+    np.testing.assert_array_equal(dz.numpy(), g[name + "_depthzero"])
+    assert np.isfinite(g[name + "_uf"]).any(), "mask selects nothing: vacuous case"
+
+
+@pytest.mark.parametrize("name", cases.CORR_CASES)
+def test_correlation(golden, name):
+    c = cases.corr_case(name)
+    y = O.local_correlation(T(c["x1"]), T(c["x2"]), 4)
+    np.testing.assert_array_equal(y.numpy(), golden("correlation")[name])
