@@ -65,7 +65,8 @@ long long dpv_launch_count(void);
  * cost  : [B, D, H, W] out
  * log_softmax_out : optional [B, D, H, W]; when non-null additionally receives
  *         log_softmax(cost, dim=1) (models/packnet.py:394 places them back to back).
- * algo  : 0 = choose, 1 = direct per-plane gather, 2 = per-cell Gram form (L2 only).
+ * algo  : 0 = choose, 1 = direct per-plane gather (L1 or L2), 2 = per-cell Gram form with global
+ *         gathers (L2), 3 = per-cell Gram form staged through shared memory (L2, production path).
  */
 int dpv_sweep_cost_volume(const float* ref, const float* src, const float* pose, const float* K,
                           const float* rays, const float* d_candi, float* cost,

@@ -82,6 +82,23 @@ __device__ __forceinline__ void sweep_coord(float t1x, float t1y, float t1z, con
     iy = __fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), half_h), 0.5f);
 }
 
+// Same mapping with one reciprocal instead of four IEEE divisions (used by the Gram kernels, whose
+// channel contraction already differs from the reference's operation order at the 1e-6 level):
+// u = Px * rcp(Pz + 1e-10); ix = ((u - cx) / cx + 1) * W/2 - 0.5 with 1/cx precomputed.  Agrees
+// with sweep_coord to ~2 ulp of the coordinate (< 1e-5 px at the model's sizes).
+__device__ __forceinline__ void sweep_coord_fast(float t1x, float t1y, float t1z, const PixelTerm& p,
+                                                 float d, float cx, float cy, float inv_cx,
+                                                 float inv_cy, float half_w, float half_h,
+                                                 float& ix, float& iy) {
+    const float px = fmaf(p.x, d, t1x);
+    const float py = fmaf(p.y, d, t1y);
+    const float pz = fmaf(p.z, d, t1z);
+    const float inv = __frcp_rn(pz + 1e-10f);
+    const float u = px * inv, v = py * inv;
+    ix = fmaf(fmaf(u - cx, inv_cx, 1.0f), half_w, -0.5f);
+    iy = fmaf(fmaf(v - cy, inv_cy, 1.0f), half_h, -0.5f);
+}
+
 // Non-finite or absurdly large coordinates are sent far outside the image so that every tap
 // is out of bounds and samples zero (the behaviour of ATen's CUDA grid sampler).
 __device__ __forceinline__ Tap make_tap(float ix, float iy) {

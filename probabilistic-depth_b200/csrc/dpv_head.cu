@@ -6,10 +6,15 @@
 //   Var[d]                 trainer/default_trainer.py:333-336
 //   argmax bin             torch.argmax (not in the reference)
 //   1/4 nearest hand-off   trainer/default_trainer.py:221-222
-// The volume is [B,D,H,W] with the bin axis strided by H*W, so a warp reading one bin of 32 (or
-// 64) consecutive pixels is a fully coalesced 128 B (256 B) request.  Each thread keeps all D
-// bins of its pixel(s) in registers: the input is read from HBM exactly once and every output
-// is written exactly once.  HBM-bound: 8*D + 16 bytes per pixel with all outputs on.
+// The volume is [B,D,H,W] with the bin axis strided by H*W.  T threads (adjacent lanes) share one
+// pixel, each keeping D/T consecutive bins in registers, so the input is read from HBM exactly
+// once and every output is written exactly once; a warp-wide load of one register slot is T runs
+// of 32/T consecutive pixels (whole 32 B sectors).  Per-pixel reductions (max, sum, mean,
+// variance, arg-max) finish with log2(T) warp shuffles.  Splitting the bins over T lanes keeps
+// the register footprint small enough for >= 50 % occupancy, which is what hides HBM latency
+// here.  HBM-bound: 8*D + 16 bytes per pixel with all outputs on.
+#include <cstdlib>
+
 #include "dpv_common.cuh"
 
 namespace dpv {
@@ -22,132 +27,173 @@ struct HeadArgs {
 
 constexpr int HEAD_NT = 128;
 
-template <int D, int VEC>
-__global__ void __launch_bounds__(HEAD_NT, 2) head_kernel(const HeadArgs a) {
+// exp2 on the SFU: one MUFU.EX2, denormal results flushed to zero.
+__device__ __forceinline__ float ex2(float t) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+template <int T>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int T>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int T>
+__device__ __forceinline__ int group_min(int v) {
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Per-element budget at the HBM rate is ~25 issue slots (2.9 elements/clk/SM at 6.5 TB/s), so the
+// soft-max is arranged around t = (x - max) * log2(e), kept in registers:
+//   sum   : S = sum ex2(t)                      (1 MUFU + 1 FADD)
+//   log p : t * ln2 - ln S                      (1 FFMA)   = (x - max) - ln S to 1-2 ulp of |x - max|
+//   p     : ex2(t - log2 S)                     (1 FADD + 1 MUFU)
+// The maximal bin has t = 0 exactly, so its log p is exactly -ln S, and the arg-max (first
+// maximum of the log-probabilities, what torch.argmax returns on this kernel's own output) is the
+// first bin whose log p equals -ln S.  (A running "best so far" chain makes the compiler keep
+// every log p live: +100 registers.)  NaN inputs are not supported.
+template <int D, int T, int MODE, bool ADD>
+__global__ void __launch_bounds__(HEAD_NT) head_kernel(const HeadArgs a) {
+    constexpr int DT = D / T;          // bins per thread
+    constexpr int PIX = HEAD_NT / T;   // pixels per CTA
     __shared__ float d_s[D];
+    // read through a volatile view: keeps the bin depths in shared memory instead of registers
+    const volatile float* d_v = d_s;
     const int HW = a.H * a.W;
     const int tid = threadIdx.x;
     for (int k = tid; k < D; k += HEAD_NT) d_s[k] = __ldg(a.d + k);
     __syncthreads();
     const int b = blockIdx.y;
-    const int q = (blockIdx.x * HEAD_NT + tid) * VEC;
-    if (q >= HW) return;
-    const long long base = (long long)b * D * HW + q;
+    const int r = tid % T;
+    int q = blockIdx.x * PIX + tid / T;
+    const bool live = q < HW;          // dead lanes keep running (shuffles) on the last pixel
+    q = live ? q : HW - 1;
+    const int kb = r * DT;
+    const long long base = ((long long)b * D + kb) * HW + q;
 
-    float v[D][VEC];
+    float v[DT];
+    {
+        const float* px = a.x + base;
+        const float* pa = ADD ? a.addend + base : nullptr;
+        constexpr int CH = (ADD && DT > 16) ? 16 : DT;   // with an addend: load and add in chunks
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        if (VEC == 2) {
-            float2 t = ld_stream2(a.x + base + (long long)k * HW);
-            v[k][0] = t.x; v[k][VEC - 1] = t.y;
-        } else {
-            v[k][0] = ld_stream(a.x + base + (long long)k * HW);
-        }
-    }
-    if (a.addend != nullptr) {
+        for (int k0 = 0; k0 < DT; k0 += CH) {
 #pragma unroll
-        for (int k = 0; k < D; ++k) {
-            if (VEC == 2) {
-                float2 t = ld_stream2(a.addend + base + (long long)k * HW);
-                v[k][0] += t.x; v[k][VEC - 1] += t.y;
-            } else {
-                v[k][0] += ld_stream(a.addend + base + (long long)k * HW);
+            for (int k = k0; k < k0 + CH; ++k) {
+                v[k] = ld_stream(px);
+                px += HW;
+                asm volatile("" : "+l"(px));   // running pointer: no table of offsets in registers
             }
-        }
-    }
-
-    float shift[VEC];   // what to subtract to get log-probabilities
+            if (ADD) {
+                float w[CH];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) shift[j] = 0.f;
-    if (a.mode == DPV_IN_LOGITS) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            float m = v[0][j];
-#pragma unroll
-            for (int k = 1; k < D; ++k) m = fmaxf(m, v[k][j]);
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                v[k][j] = v[k][j] - m;
-                s += expf(v[k][j]);
-            }
-            shift[j] = logf(s);
-        }
-    }
-
-    // Pass 3: log-probabilities out, probabilities kept in registers, E[d], arg-max.
-    float mean[VEC];
-    int best_k[VEC];
-    float best[VEC];
-    const bool is_prob = (a.mode == DPV_IN_PROB);
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) { mean[j] = 0.f; best_k[j] = 0; best[j] = -INFINITY; }
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        float lp[VEC], pr[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            if (is_prob) {
-                pr[j] = v[k][j];
-                lp[j] = v[k][j];   // arg-max is taken over the values as given
-            } else {
-                lp[j] = v[k][j] - shift[j];
-                pr[j] = expf(lp[j]);
-            }
-            // torch.argmax: first maximum wins, NaN counts as the maximum
-            const bool take = (lp[j] > best[j]) || (lp[j] != lp[j] && best[j] == best[j]) || (k == 0);
-            best_k[j] = take ? k : best_k[j];
-            best[j] = take ? lp[j] : best[j];
-            mean[j] = fmaf(d_s[k], pr[j], mean[j]);
-            v[k][j] = pr[j];
-        }
-        if (a.logp != nullptr) {
-            float* o = a.logp + base + (long long)k * HW;
-            if (is_prob) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) lp[j] = logf(pr[j]);
-            }
-            if (VEC == 2) st_stream2(o, make_float2(lp[0], lp[VEC - 1])); else st_stream(o, lp[0]);
-        }
-        if (a.prob != nullptr) {
-            float* o = a.prob + base + (long long)k * HW;
-            if (VEC == 2) st_stream2(o, make_float2(pr[0], pr[VEC - 1])); else st_stream(o, pr[0]);
-        }
-        if (a.quarter != nullptr) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const int qq = q + j, y = qq / a.W, xx = qq - y * a.W;
-                const int h4 = a.H / 4, w4 = a.W / 4;
-                if (qq < HW && (y & 3) == 0 && (xx & 3) == 0 && (y >> 2) < h4 && (xx >> 2) < w4) {
-                    const float val = is_prob ? pr[j] : lp[j];
-                    a.quarter[((long long)b * D + k) * h4 * w4 + (y >> 2) * w4 + (xx >> 2)] = val;
+                for (int k = 0; k < CH; ++k) {
+                    w[k] = ld_stream(pa);
+                    pa += HW;
+                    asm volatile("" : "+l"(pa));
                 }
+#pragma unroll
+                for (int k = 0; k < CH; ++k) v[k0 + k] += w[k];
             }
         }
     }
+
+    float ln_s = 0.f, log2_s = 0.f, top;
+    if (MODE == DPV_IN_LOGITS) {
+        float m = v[0];
+#pragma unroll
+        for (int k = 1; k < DT; ++k) m = fmaxf(m, v[k]);
+        m = group_max<T>(m);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            v[k] = (v[k] - m) * kLog2e;
+            s += ex2(v[k]);
+        }
+        s = group_sum<T>(s);
+        ln_s = logf(s);
+        log2_s = ln_s * kLog2e;
+        top = -ln_s;
+    } else {
+        top = v[0];
+#pragma unroll
+        for (int k = 1; k < DT; ++k) top = fmaxf(top, v[k]);
+        top = group_max<T>(top);
+    }
+
+    // 1/4-resolution hand-off: is this pixel kept, and where does it go
+    const int h4 = a.H / 4, w4 = a.W / 4;
+    bool q_keep = false;
+    long long qoff = 0;
+    if (a.quarter != nullptr) {
+        const int y = q / a.W, xx = q - y * a.W;
+        q_keep = live && ((y & 3) == 0) && ((xx & 3) == 0) && ((y >> 2) < h4) && ((xx >> 2) < w4);
+        qoff = ((long long)b * D + kb + (DT - 1)) * h4 * w4 + (y >> 2) * w4 + (xx >> 2);
+    }
+
+    // Main pass, last bin first so that the smallest index among equal maxima is what remains.
+    const bool has_logp = (a.logp != nullptr) && live, has_prob = (a.prob != nullptr) && live;
+    long long off = base + (long long)(DT - 1) * HW;
+    float mean = 0.f;
+    int best_k = 1 << 30;
+#pragma unroll
+    for (int kk = 0; kk < DT; ++kk) {
+        const int k = DT - 1 - kk;
+        const float dk = d_v[kb + k];
+        float lp, pr;
+        if (MODE == DPV_IN_PROB) {
+            pr = v[k];
+            lp = pr;                              // arg-max over the values as given
+        } else if (MODE == DPV_IN_LOGPROB) {
+            lp = v[k];
+            pr = ex2(lp * kLog2e);
+        } else {
+            lp = fmaf(v[k], kLn2, -ln_s);
+            pr = ex2(v[k] - log2_s);
+        }
+        best_k = (lp == top) ? (kb + k) : best_k;
+        mean = fmaf(dk, pr, mean);
+        v[k] = pr;
+        if (has_logp) st_stream(a.logp + off, (MODE == DPV_IN_PROB) ? logf(pr) : lp);
+        if (has_prob) st_stream(a.prob + off, pr);
+        off -= HW;
+        asm volatile("" : "+l"(off));
+        if (q_keep) {
+            a.quarter[qoff] = (MODE == DPV_IN_PROB) ? pr : lp;
+            qoff -= h4 * w4;
+        }
+    }
+    mean = group_sum<T>(mean);
+    best_k = group_min<T>(best_k);
 
     const long long pix = (long long)b * HW + q;
-    if (a.depth != nullptr) {
-        if (VEC == 2) st_stream2(a.depth + pix, make_float2(mean[0], mean[VEC - 1]));
-        else a.depth[pix] = mean[0];
-    }
+    const bool writer = live && (r == 0);
     if (a.var != nullptr) {
-        float var[VEC];
+        float var = 0.f;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            var[j] = 0.f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const float c = d_s[k] - mean[j];
-                var[j] = fmaf(c * c, v[k][j], var[j]);
-            }
+        for (int k = 0; k < DT; ++k) {
+            const float c = d_v[kb + k] - mean;
+            var = fmaf(c * c, v[k], var);
         }
-        if (VEC == 2) st_stream2(a.var + pix, make_float2(var[0], var[VEC - 1]));
-        else a.var[pix] = var[0];
+        var = group_sum<T>(var);
+        if (writer) a.var[pix] = var;
     }
-    if (a.argmax != nullptr) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) a.argmax[pix + j] = (long long)best_k[j];
+    if (writer) {
+        if (a.depth != nullptr) a.depth[pix] = mean;
+        if (a.argmax != nullptr) a.argmax[pix] = (long long)(best_k == (1 << 30) ? 0 : best_k);
     }
 }
 
@@ -177,7 +223,7 @@ __global__ void __launch_bounds__(HEAD_NT) head_generic_kernel(const HeadArgs a)
     for (int k = 0; k < D; ++k) {
         float lp, pr;
         if (is_prob) { pr = in(k); lp = pr; } else { lp = (in(k) - m) - shift; pr = expf(lp); }
-        const bool take = (lp > best) || (lp != lp && best == best) || (k == 0);
+        const bool take = (lp > best) || (k == 0);
         best_k = take ? k : best_k;
         best = take ? lp : best;
         mean = fmaf(__ldg(a.d + k), pr, mean);
@@ -204,13 +250,41 @@ __global__ void __launch_bounds__(HEAD_NT) head_generic_kernel(const HeadArgs a)
     if (a.argmax != nullptr) a.argmax[pix] = (long long)best_k;
 }
 
-template <int D, int VEC>
-static int launch_head(const HeadArgs& a, cudaStream_t st) {
+static const int g_head_t = [] { const char* e = getenv("DPV_HEAD_T"); return e ? atoi(e) : 0; }();
+
+template <int D, int T>
+static int launch_head_t(const HeadArgs& a, cudaStream_t st) {
     const int HW = a.H * a.W;
-    dim3 grid((HW + HEAD_NT * VEC - 1) / (HEAD_NT * VEC), a.B), block(HEAD_NT);
-    head_kernel<D, VEC><<<grid, block, 0, st>>>(a);
+    constexpr int PIX = HEAD_NT / T;
+    dim3 grid((HW + PIX - 1) / PIX, a.B), block(HEAD_NT);
+    if (a.mode == DPV_IN_LOGITS && a.addend) head_kernel<D, T, DPV_IN_LOGITS, true><<<grid, block, 0, st>>>(a);
+    else if (a.mode == DPV_IN_LOGITS) head_kernel<D, T, DPV_IN_LOGITS, false><<<grid, block, 0, st>>>(a);
+    else if (a.mode == DPV_IN_LOGPROB) head_kernel<D, T, DPV_IN_LOGPROB, false><<<grid, block, 0, st>>>(a);
+    else head_kernel<D, T, DPV_IN_PROB, false><<<grid, block, 0, st>>>(a);
     DPV_LAUNCH_END();
     return 0;
+}
+
+// Threads per pixel.  Measured on B200 at D = 64, 8 x 256 x 384 pixels: T = 1 (96 registers, 5
+// CTAs/SM, 128 B runs per request) 5.3 TB/s, T = 2 5.2 TB/s, T = 4 4.1 TB/s, T = 8 2.5 TB/s.  Small
+// volumes (the 1/4-resolution DPV) split the bins to put more warps on the chip.
+template <int D>
+static int launch_head(const HeadArgs& a, cudaStream_t st) {
+    const long long pixels = (long long)a.B * a.H * a.W;
+    int t = (D > 64) ? D / 64 : 1;
+    if (pixels < 148LL * 1024) t = max(t, 2);
+    if (pixels < 148LL * 256) t = max(t, 4);
+    if (g_head_t == 1 || g_head_t == 2 || g_head_t == 4 || g_head_t == 8) t = g_head_t;
+    if (D / t > 64) t = D / 64;
+    if (D / t < 4) t = D / 4;
+    switch (t) {
+        case 1: if constexpr (D <= 64) return launch_head_t<D, 1>(a, st); break;
+        case 2: if constexpr (D <= 128 && D >= 8) return launch_head_t<D, 2>(a, st); break;
+        case 4: if constexpr (D >= 16) return launch_head_t<D, 4>(a, st); break;
+        case 8: if constexpr (D >= 32) return launch_head_t<D, 8>(a, st); break;
+        default: break;
+    }
+    return DPV_E_UNSUPP;
 }
 
 }  // namespace dpv
@@ -229,13 +303,12 @@ extern "C" int dpv_head(const float* x, const float* addend, const float* d_cand
     a.B = B; a.D = D; a.H = H; a.W = W; a.mode = in_mode;
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
-    const uintptr_t bits = (uintptr_t)x | (uintptr_t)addend | (uintptr_t)logp | (uintptr_t)prob |
-                           (uintptr_t)depth | (uintptr_t)variance;
-    const bool pair = (HW % 2 == 0) && ((bits & 7) == 0);   // 8-byte vector accesses
     switch (D) {
-        case 16: return pair ? launch_head<16, 2>(a, st) : launch_head<16, 1>(a, st);
-        case 32: return pair ? launch_head<32, 2>(a, st) : launch_head<32, 1>(a, st);
-        case 64: return pair ? launch_head<64, 2>(a, st) : launch_head<64, 1>(a, st);
+        case 16: return launch_head<16>(a, st);
+        case 32: return launch_head<32>(a, st);
+        case 64: return launch_head<64>(a, st);
+        case 128: return launch_head<128>(a, st);
+        case 256: return launch_head<256>(a, st);
         default: break;
     }
     dim3 grid((HW + HEAD_NT - 1) / HEAD_NT, B), block(HEAD_NT);

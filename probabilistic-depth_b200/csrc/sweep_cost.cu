@@ -17,38 +17,12 @@
 //             so the channel contraction is done once per (pixel, cell) as a 4x4 Gram matrix of
 //             differences (10 sums, no cancellation: every term is built from differences),
 //             and every further plane in that cell costs a 10-term quadratic form.
-#include "dpv_common.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+#include "sweep_common.cuh"
 
 namespace dpv {
-
-struct SweepArgs {
-    const float* ref; const float* src; const float* pose; const float* K; const float* rays;
-    const float* d; float* cost; float* lsm;
-    int B, V, C, D, H, W, PS;
-    long long ref_bs, src_bs, src_vs, pose_bs, k_bs, rays_bs;
-    float sigma;
-};
-
-struct CellTaps {
-    int o00, o01, o10, o11;      // element offsets inside one channel plane (0 when invalid)
-    bool v00, v01, v10, v11;
-    int id;                      // cell identity for run detection
-};
-
-__device__ __forceinline__ CellTaps cell_taps(const Tap& t, int H, int W) {
-    CellTaps c;
-    bool xl = (t.x0 >= 0) & (t.x0 < W), xr = (t.x0 + 1 >= 0) & (t.x0 + 1 < W);
-    bool yt = (t.y0 >= 0) & (t.y0 < H), yb = (t.y0 + 1 >= 0) & (t.y0 + 1 < H);
-    c.v00 = xl & yt; c.v01 = xr & yt; c.v10 = xl & yb; c.v11 = xr & yb;
-    int base = t.y0 * W + t.x0;
-    c.o00 = c.v00 ? base : 0;
-    c.o01 = c.v01 ? base + 1 : 0;
-    c.o10 = c.v10 ? base + W : 0;
-    c.o11 = c.v11 ? base + W + 1 : 0;
-    bool any = c.v00 | c.v01 | c.v10 | c.v11;
-    c.id = any ? (t.y0 + 2) * (W + 4) + (t.x0 + 2) : -1;   // all-outside cells are one cell
-    return c;
-}
 
 template <int NT>
 __global__ void __launch_bounds__(NT) sweep_gram_kernel(const SweepArgs a) {
@@ -60,12 +34,19 @@ __global__ void __launch_bounds__(NT) sweep_gram_kernel(const SweepArgs a) {
     const int nk = k1 - k0;
     float* cost_s = smem;                 // [nk][NT]
     float* d_s = smem + kper * NT;        // [kper]
-    const int b = blockIdx.z;
     const int tid = threadIdx.x;
-    const int p = blockIdx.x * NT + tid;
     for (int k = tid; k < nk; k += NT) d_s[k] = __ldg(a.d + k0 + k);
     __syncthreads();
-    if (p >= HW || nk <= 0) return;
+    if (nk <= 0) return;
+    // Persistent over (item, pixel block) tiles: the number of resident warps per SM is chosen by
+    // the launcher so that their combined footprint (C channel planes x a few 128 B lines each)
+    // stays inside L1; consecutive tiles of a warp are neighbours in the image.
+    const int blocks_per_item = (HW + NT - 1) / NT;
+    const int ntiles = blocks_per_item * a.B;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / blocks_per_item;
+    const int p = (tile - b * blocks_per_item) * NT + tid;
+    if (p >= HW) continue;
 
     const float* rays = a.rays + (long long)b * a.rays_bs;
     const float rx = __ldg(rays + p), ry = __ldg(rays + HW + p), rz = __ldg(rays + 2 * HW + p);
@@ -109,8 +90,14 @@ __global__ void __launch_bounds__(NT) sweep_gram_kernel(const SweepArgs a) {
                     rp += HW; s00 += HW; s01 += HW; s10 += HW; s11 += HW;
                 }
             }
-            // ---- every plane whose sample falls into this cell
+            // ---- every plane whose sample falls into this cell.  A sample within kCellSlack of
+            // the cell border stays in the cell with a fraction marginally outside [0,1]: the
+            // bilinear interpolant is continuous across cells, so this changes the value by
+            // <= slack * |second difference|, the same order as the fp32 rounding of the
+            // coordinate itself, and it stops a rectified pair (v = row centre +- 1 ulp, floor
+            // flipping between two rows from plane to plane) from opening a new cell per plane.
             const int id = cell.id;
+            const float cx0 = (float)tap.x0, cy0 = (float)tap.y0;
             do {
                 float nw, ne, sw, se;
                 bilinear_weights(tap, nw, ne, sw, se);
@@ -125,6 +112,12 @@ __global__ void __launch_bounds__(NT) sweep_gram_kernel(const SweepArgs a) {
                     sweep_coord(t1x, t1y, t1z, pt, d_s[k], cx, cy, half_w, half_h, ix, iy);
                     tap = make_tap(ix, iy);
                     cell = cell_taps(tap, a.H, a.W);
+                    const float rx0 = ix - cx0, ry0 = iy - cy0;
+                    if (id >= 0 && cell.id != id && rx0 >= -kCellSlack && rx0 <= 1.0f + kCellSlack &&
+                        ry0 >= -kCellSlack && ry0 <= 1.0f + kCellSlack) {
+                        tap.x0 = (int)cx0; tap.y0 = (int)cy0; tap.fx = rx0; tap.fy = ry0;
+                        cell.id = id;
+                    }
                 }
             } while (k < nk && cell.id == id);
         }
@@ -141,6 +134,7 @@ __global__ void __launch_bounds__(NT) sweep_gram_kernel(const SweepArgs a) {
         float* lo = a.lsm + ((long long)b * a.D + k0) * HW + p;
         for (int k = 0; k < nk; ++k) lo[(long long)k * HW] = (cost_s[k * NT + tid] - m) - ls;
     }
+    }   // tile loop
 }
 
 template <int NT, int DIST>
@@ -232,10 +226,11 @@ extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const f
     DPV_CHECK_ARG(ref && src && pose && K && rays && d_candi && cost);
     DPV_CHECK_ARG(B > 0 && V > 0 && C > 0 && D > 0 && H > 0 && W > 0);
     DPV_CHECK_ARG(dist == DPV_DIST_L2 || dist == DPV_DIST_L1);
-    DPV_CHECK_ARG(algo >= 0 && algo <= 2);
+    DPV_CHECK_ARG(algo >= 0 && algo <= 3);
     if ((long long)H * W > (1LL << 30) || B > 65535) return DPV_E_UNSUPP;
-    if (algo == 2 && dist != DPV_DIST_L2) return DPV_E_UNSUPP;
-    if (algo == 0) algo = (dist == DPV_DIST_L2) ? 2 : 1;
+    if (algo >= 2 && dist != DPV_DIST_L2) return DPV_E_UNSUPP;
+    if (algo == 3 && log_softmax_out != nullptr) return DPV_E_UNSUPP;
+    if (algo == 0) algo = (dist != DPV_DIST_L2) ? 1 : (log_softmax_out != nullptr ? 2 : 3);
     constexpr int NT = 32;
     SweepArgs a;
     a.ref = ref; a.src = src; a.pose = pose; a.K = K; a.rays = rays; a.d = d_candi;
@@ -246,6 +241,7 @@ extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const f
     a.sigma = sigma;
     const int HW = H * W;
     a.PS = pick_plane_split(B, HW, D, log_softmax_out != nullptr);
+    if (algo == 3) return launch_sweep_gram_tiled(a, (cudaStream_t)stream);
     const int kper = (D + a.PS - 1) / a.PS;
     const size_t smem = (size_t)kper * (NT + 1) * sizeof(float);
     if (smem > 200 * 1024) return DPV_E_UNSUPP;
@@ -256,7 +252,12 @@ extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const f
         if (smem > 48 * 1024)
             e = cudaFuncSetAttribute(sweep_gram_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        sweep_gram_kernel<NT><<<grid, block, smem, st>>>(a);
+        static const int wps = [] { const char* v = getenv("DPV_SWEEP_WPS"); return v ? atoi(v) : 0; }();
+        const int ntiles = grid.x * B;
+        int gx = ntiles;
+        if (wps > 0) gx = std::min(ntiles, std::max(1, 148 * wps / a.PS));
+        dim3 pgrid(gx, a.PS, 1);
+        sweep_gram_kernel<NT><<<pgrid, block, smem, st>>>(a);
     } else if (dist == DPV_DIST_L2) {
         if (smem > 48 * 1024)
             e = cudaFuncSetAttribute(sweep_direct_kernel<NT, DPV_DIST_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -43,44 +43,75 @@ __device__ __forceinline__ float band_weight(const UfArgs& a, const float* __res
     return w;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) ufield_partial_kernel(const UfArgs a) {
-    extern __shared__ float acc_s[];   // [D][NT]
-    const int tid = threadIdx.x;
-    const int x = blockIdx.x * NT + tid;
-    const int chunk = blockIdx.y;
-    const int b = blockIdx.z;
-    if (x >= a.W) return;
+constexpr int UF_COLS = 32;    // columns per CTA (one warp-width: 128 B rows of the volume)
+constexpr int UF_GROUPS = 8;   // warps per CTA, each owning D/8 consecutive bins
+constexpr int UF_ROWS = 32;    // image rows per CTA (one partial sum per chunk of rows)
+
+// One CTA = 32 columns x 32 rows of one item.  Step 1: all 256 threads evaluate the per-pixel
+// weights once into shared memory (both roles of a row index: as a shifted-frame row for the
+// denominator, as an image row for the numerator).  Step 2: warp g accumulates bins
+// [g*DB, (g+1)*DB) in registers over the rows whose weight is non-zero; rows off the road band
+// cost nothing, and a row on the band is DB coalesced 128 B loads per warp.
+template <int DB>
+__global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_partial_kernel(const UfArgs a) {
+    __shared__ float w_s[UF_ROWS][UF_COLS];     // numerator weight of image pixel (r, x)
+    __shared__ float z_s[UF_ROWS][UF_COLS];     // denominator weight of shifted pixel (r, x)
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int x = blockIdx.x * UF_COLS + lane;
+    const int chunk = blockIdx.y, b = blockIdx.z;
     const int HW = a.H * a.W;
     const float* depth_b = a.depth + (long long)b * HW;
     const float* mask_b = a.mask ? a.mask + (long long)b * HW : nullptr;
-    const float* dpv_b = a.dpv + (long long)b * a.D * HW;
     const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
-    for (int k = 0; k < a.D; ++k) acc_s[k * NT + tid] = 0.f;
-    float cnt = 0.f;
-    const int r0 = chunk * a.rows_per_chunk, r1 = min(a.H, r0 + a.rows_per_chunk);
-    const int xi = a.col_inv[x];
-    for (int r = r0; r < r1; ++r) {
-        cnt = __fadd_rn(cnt, band_weight(a, depth_b, mask_b, r, x, fy, cy));   // role: shifted row
-        const int yi = a.row_inv[r];                                            // role: image row
-        float w = 0.f;
-        if (yi >= 0 && xi >= 0) w = band_weight(a, depth_b, mask_b, yi, xi, fy, cy);
-        if (a.depth_zero != nullptr)
-            a.depth_zero[(long long)b * HW + r * a.W + x] = __fmul_rn(__ldg(depth_b + r * a.W + x), w);
+    const int r0 = chunk * UF_ROWS;
+    const bool col_ok = x < a.W;
+    const int xi = col_ok ? a.col_inv[x] : -1;
+    for (int rr = grp; rr < UF_ROWS; rr += UF_GROUPS) {
+        const int r = r0 + rr;
+        float wz = 0.f, w = 0.f;
+        if (col_ok && r < a.H) {
+            wz = band_weight(a, depth_b, mask_b, r, x, fy, cy);
+            const int yi = a.row_inv[r];
+            if (yi >= 0 && xi >= 0) w = band_weight(a, depth_b, mask_b, yi, xi, fy, cy);
+            if (a.depth_zero != nullptr)
+                a.depth_zero[(long long)b * HW + r * a.W + x] = __fmul_rn(__ldg(depth_b + r * a.W + x), w);
+        }
+        z_s[rr][lane] = wz;
+        w_s[rr][lane] = w;
+    }
+    __syncthreads();
+    if (grp == 0 && col_ok) {
+        float cnt = 0.f;
+        for (int rr = 0; rr < UF_ROWS; ++rr) cnt = __fadd_rn(cnt, z_s[rr][lane]);
+        a.cnt[((long long)b * a.nchunk + chunk) * a.W + x] = cnt;
+    }
+    const int kb = grp * DB;
+    if (kb >= a.D) return;
+    float acc[DB];
+#pragma unroll
+    for (int j = 0; j < DB; ++j) acc[j] = 0.f;
+    const float* dpv_b = a.dpv + ((long long)b * a.D + kb) * HW + x;
+    for (int rr = 0; rr < UF_ROWS; ++rr) {
+        const float w = w_s[rr][lane];
+        if (!__any_sync(0xffffffffu, w != 0.f)) continue;
         if (w != 0.f) {
-            const float* col = dpv_b + r * a.W + x;
-            if (a.mode == DPV_IN_PROB) {
-                for (int k = 0; k < a.D; ++k)
-                    acc_s[k * NT + tid] = __fadd_rn(acc_s[k * NT + tid], __fmul_rn(ld_stream(col + (long long)k * HW), w));
-            } else {
-                for (int k = 0; k < a.D; ++k)
-                    acc_s[k * NT + tid] = __fadd_rn(acc_s[k * NT + tid], __fmul_rn(expf(ld_stream(col + (long long)k * HW)), w));
+            const float* col = dpv_b + (long long)(r0 + rr) * a.W;
+            float v[DB];
+#pragma unroll
+            for (int j = 0; j < DB; ++j) v[j] = (kb + j < a.D) ? ld_stream(col + (long long)j * HW) : 0.f;
+#pragma unroll
+            for (int j = 0; j < DB; ++j) {
+                const float pr = (a.mode == DPV_IN_PROB) ? v[j] : expf(v[j]);
+                acc[j] = __fadd_rn(acc[j], __fmul_rn(pr, w));
             }
         }
     }
-    float* part = a.part + (((long long)b * a.nchunk + chunk) * a.D) * a.W + x;
-    for (int k = 0; k < a.D; ++k) part[(long long)k * a.W] = acc_s[k * NT + tid];
-    a.cnt[((long long)b * a.nchunk + chunk) * a.W + x] = cnt;
+    if (col_ok) {
+        float* part = a.part + (((long long)b * a.nchunk + chunk) * a.D + kb) * a.W + x;
+#pragma unroll
+        for (int j = 0; j < DB; ++j)
+            if (kb + j < a.D) part[(long long)j * a.W] = acc[j];
+    }
 }
 
 __global__ void __launch_bounds__(128) ufield_finish_kernel(const UfArgs a) {
@@ -97,10 +128,7 @@ __global__ void __launch_bounds__(128) ufield_finish_kernel(const UfArgs a) {
 
 }  // namespace dpv
 
-static int ufield_row_chunks(int H) {
-    const int rows = 16;
-    return (H + rows - 1) / rows;
-}
+static int ufield_row_chunks(int H) { return (H + dpv::UF_ROWS - 1) / dpv::UF_ROWS; }
 
 extern "C" int64_t dpv_ufield_workspace_floats(int B, int D, int H, int W) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
@@ -119,23 +147,26 @@ extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_c
     DPV_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0);
     DPV_CHECK_ARG(in_mode == DPV_IN_LOGPROB || in_mode == DPV_IN_PROB);
     if (B > 65535 || D > 65535) return DPV_E_UNSUPP;
-    constexpr int NT = 64;
-    if ((size_t)D * NT * sizeof(float) > 48 * 1024) return DPV_E_UNSUPP;
+    if (D > 32 * UF_GROUPS) return DPV_E_UNSUPP;
     UfArgs a;
     a.dpv = dpv; a.depth = depth; a.d = d_candi; a.intr = intr_up; a.mask = mask;
     a.row_fwd = row_fwd; a.row_inv = row_inv; a.col_fwd = col_fwd; a.col_inv = col_inv;
     a.uf = uf; a.depth_zero = depth_zero;
     a.B = B; a.D = D; a.H = H; a.W = W; a.mode = in_mode;
     a.nchunk = ufield_row_chunks(H);
-    a.rows_per_chunk = (H + a.nchunk - 1) / a.nchunk;
+    a.rows_per_chunk = UF_ROWS;
     a.part = workspace;
     a.cnt = workspace + (long long)B * a.nchunk * D * W;
     a.intr_bs = intr_bstride;
     a.zstart = zstart; a.zend = zend; a.maxd1 = maxd - 1.0f; a.mind = mind;
     a.pad_depth = pad_depth;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((W + NT - 1) / NT, a.nchunk, B), block(NT);
-    ufield_partial_kernel<NT><<<grid, block, (size_t)D * NT * sizeof(float), st>>>(a);
+    dim3 grid((W + UF_COLS - 1) / UF_COLS, a.nchunk, B), block(UF_COLS * UF_GROUPS);
+    const int db = (D + UF_GROUPS - 1) / UF_GROUPS;
+    if (db <= 4) ufield_partial_kernel<4><<<grid, block, 0, st>>>(a);
+    else if (db <= 8) ufield_partial_kernel<8><<<grid, block, 0, st>>>(a);
+    else if (db <= 16) ufield_partial_kernel<16><<<grid, block, 0, st>>>(a);
+    else ufield_partial_kernel<32><<<grid, block, 0, st>>>(a);
     DPV_LAUNCH_END();
     dim3 grid2((W + 127) / 128, D, B), block2(128);
     ufield_finish_kernel<<<grid2, block2, 0, st>>>(a);

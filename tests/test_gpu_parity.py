@@ -9,8 +9,9 @@ depth and variance within 1e-4 relative in fp32"):
   argmax                    exact
   UF                        same NaN pattern, rtol 1e-4 on columns without a pixel within 1e-4 of a
                             mask threshold (a flipped pixel changes a column discretely)
-  correlation               atol 2e-7 (the reference's own bar is atol 1e-7 between its CUDA and
-                            torch versions, models/correlation_native.py:64; summation order differs)
+  correlation               atol 2e-7 + rtol 1e-6 (the reference's own bar is atol 1e-7 between its
+                            CUDA and torch versions on C>=128 inputs, i.e. |values| ~ 0.1,
+                            models/correlation_native.py:64; summation order differs, 2 ulp)
 """
 import numpy as np
 import pytest
@@ -49,7 +50,7 @@ def cam_dict(c):
 
 # ------------------------------------------------------------------------- K1 + K2a
 @pytest.mark.parametrize("name", cases.SWEEP_CASES)
-@pytest.mark.parametrize("dist,algo", [("L2", 2), ("L2", 1), ("L1", 1)])
+@pytest.mark.parametrize("dist,algo", [("L2", 3), ("L2", 2), ("L2", 1), ("L1", 1)])
 def test_sweep_vs_golden(dpv, golden, name, dist, algo):
     g = golden("sweep")
     key = "%s_%s" % (name, dist)
@@ -114,7 +115,7 @@ def test_sweep_identity_pose_is_near_zero(dpv):
     ref = synth.randn(5, 1, C, h, w)
     poses = synth.pose()[None, None]
     cam = synth.camera(w, h, 1)
-    for algo in (1, 2):
+    for algo in (1, 2, 3):
         cost = dpv.ops.sweep_cost_volume(cu(ref), cu(ref[:, None]), cu(poses), cu(cam["intrinsics"]),
                                          cu(cam["unit_ray"]), synth.depth_candidates(5, 40, D), 10.0,
                                          algo=algo)
@@ -236,7 +237,8 @@ def _near_threshold_columns(c, log):
     pts = O.depth_to_points(z, T(c["intr_up"]))
     bad = torch.zeros((H, W), dtype=torch.bool)
     for val, thr in ((pts[1], 0.9), (pts[1], 0.6), (pts[2], 99.0), (pts[2], 0.0)):
-        bad |= (val - thr).abs() <= 1e-4 * max(1.0, abs(thr))
+        gap = (val - thr).abs()
+        bad |= (gap > 0) & (gap <= 1e-4 * max(1.0, abs(thr)))   # exact hits (zero padding) are not rounding-sensitive
     cols = bad.any(0)
     # the mask is shifted back up by 5 rows and keeps its column: same column index
     return cols.numpy()
@@ -270,13 +272,13 @@ def test_correlation(dpv, golden, name):
     want = golden("correlation")[name]
     native = dpv.models.correlation_native.Correlation(max_displacement=4)
     got = native(cu(c["x1"]), cu(c["x2"]))
-    close(got, want, rtol=0, atol=2e-7)
+    close(got, want, rtol=1e-6, atol=2e-7)
     ext = dpv.models.correlation_package.correlation.Correlation(
         pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
     assert torch.equal(ext(cu(c["x1"]), cu(c["x2"])), got)
     # generic-radius kernel against the oracle
     got3 = dpv.ops.correlation(cu(c["x1"]), cu(c["x2"]), 2)
-    close(got3, O.local_correlation(T(c["x1"]), T(c["x2"]), 2).numpy(), rtol=0, atol=2e-7)
+    close(got3, O.local_correlation(T(c["x1"]), T(c["x2"]), 2).numpy(), rtol=1e-6, atol=2e-7)
 
 
 def test_correlation_linearity_full_size(dpv):

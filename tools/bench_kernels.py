@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Per-kernel timing (CUDA events, inputs rotated so every launch misses L2).  Dev tool."""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+dpv = importlib.import_module("probabilistic-depth_b200")
+ops = dpv.ops
+PEAK = 6554.9
+
+
+def timeit(fn, nrot, iters=20, warm=3):
+    for i in range(warm):
+        fn(i % nrot)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for i, (a, b) in enumerate(evs):
+        a.record()
+        fn(i % nrot)
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=8)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--pose", default="stereo")
+    args = ap.parse_args()
+    B, V, C, D, h, w, H, W = args.B, 1, 67, 64, 64, 96, 256, 384
+    s = dpv.synth
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(w, h, B)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    K, rays, Ku = cu(cam["intrinsics"]), cu(cam["unit_ray"]), cu(cam["intrinsics_up"])
+    poses = cu(s.stereo_poses(B) if args.pose == "stereo" else s.mono_poses(B))
+    res = {}
+
+    def want(n):
+        return not args.only or n in args.only.split(",")
+
+    nrot = 3
+    if want("sweep"):
+        feats = [torch.randn((B, V + 1, C, h, w), device="cuda") for _ in range(nrot)]
+        for algo in (3, 2, 1):
+            f = lambda i: ops.sweep_cost_volume(feats[i][:, -1], feats[i][:, :-1], poses[:, :-1], K, rays, d, 10.0, algo=algo)
+            med, best = timeit(f, nrot, iters=10 if algo == 1 else 20)
+            byt = B * (4 * h * w * (C * (1 + V) + D) + 12 * h * w)
+            res["sweep_algo%d" % algo] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+    if want("head"):
+        xs = [torch.randn((B, D, H, W), device="cuda") * 3 for _ in range(nrot)]
+        f = lambda i: ops.head(xs[i], d, logp=True, depth=True, variance=True, argmax=True, quarter=True)
+        med, best = timeit(f, nrot)
+        byt = B * (8 * H * W * D + 16 * H * W)
+        res["head_full"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        f = lambda i: ops.head(xs[i], d, logp=True)
+        med, best = timeit(f, nrot)
+        byt = B * (8 * H * W * D)
+        res["head_full_logp_only"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        xq = [torch.randn((B, D, h, w), device="cuda") * 3 for _ in range(nrot)]
+        f = lambda i: ops.head(xq[i], d, logp=True)
+        med, best = timeit(f, nrot)
+        byt = B * (8 * h * w * D)
+        res["head_quarter"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        # plain copy of the same volume for reference
+        ys = [torch.empty_like(xs[0]) for _ in range(nrot)]
+        f = lambda i: ys[i].copy_(xs[i])
+        med, best = timeit(f, nrot)
+        byt = B * (8 * H * W * D)
+        res["torch_copy_same_bytes"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+    if want("ufield"):
+        lg = cu(s.ground_plane_logits(2, B, H, W, d, cam["intrinsics_up"][0]))
+        hd = ops.head(lg, d, logp=True, depth=True)
+        lps = [hd["logp"].clone() for _ in range(nrot)]
+        f = lambda i: ops.ufield(lps[i], d, Ku, depth=hd["depth"])
+        med, best = timeit(f, nrot)
+        byt = B * (4 * H * W * D + 4 * D * W + 8 * H * W)
+        res["ufield_given_depth"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        f = lambda i: ops.ufield(lps[i], d, Ku)
+        med, best = timeit(f, nrot)
+        res["ufield_standalone"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+    if want("fuse"):
+        bv = [torch.log_softmax(torch.randn((B, D, h, w), device="cuda"), 1) for _ in range(nrot)]
+        dm, mk = s.sparse_depth(3, B, h, w)
+        dm, mk = cu(dm), cu(mk)
+        f = lambda i: ops.bayes_fuse(bv[i], d, dmaps=dm, masks=mk)
+        med, best = timeit(f, nrot)
+        byt = B * (12 * h * w * D + 8 * h * w)
+        res["bayes_fuse"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        fr = [torch.randn((B, 2, D, h, w), device="cuda") for _ in range(nrot)]
+        f = lambda i: ops.warp_feature(fr[i], poses, K, rays, d)
+        med, best = timeit(f, nrot)
+        byt = B * (8 * h * w * D * 2 + 12 * h * w)
+        res["warp_feature"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+    if want("corr"):
+        x1 = [torch.randn((2, 32, 96, 208), device="cuda") for _ in range(nrot)]
+        x2 = [torch.randn((2, 32, 96, 208), device="cuda") for _ in range(nrot)]
+        f = lambda i: ops.correlation(x1[i], x2[i], 4)
+        med, best = timeit(f, nrot)
+        byt = 2 * 4 * 96 * 208 * (2 * 32 + 81)
+        res["corr_2x32x96x208"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+    for k, v in res.items():
+        print("%-26s %8.4f ms (best %8.4f)  %8.1f GB/s  %5.1f%% of %.0f" % (k, v["ms"], v["best_ms"], v["GBs"], 100 * v["frac"], PEAK))
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
