@@ -143,6 +143,27 @@ int dpv_ufield(const float* dpv, const float* depth, const float* d_candi, const
                float zstart, float zend, float maxd, float mind, float pad_depth,
                void* stream);
 
+/* ---- K3 + K5 fused : depth-bin head with the uncertainty field accumulated in the same pass ----
+ * dpv_head (log-softmax, E[d], Var, arg-max, 1/4 hand-off; utils/img_utils.py:52-61,
+ * models/models.py:351, trainer/default_trainer.py:221-222,333-336) and gen_ufield
+ * (utils/img_utils.py:268-358) in one read of x [B,D,H,W] (in_mode DPV_IN_LOGITS or DPV_IN_LOGPROB):
+ * the trainer calls them back to back on the refined DPV (trainer/default_trainer.py:232-244).
+ * No ground-truth mask (that variant is dpv_ufield).  D in {32,64,128,256}, W % 4 == 0, else
+ * DPV_E_UNSUPP.  row_tab [H][4] / col_tab [W] int32 DEVICE tables: build them on the host with
+ * dpv_uf_fused_tables from the same four index maps dpv_ufield takes (HOST pointers there), which
+ * returns DPV_E_UNSUPP when the shifts do not compose to "same pixel or padding".
+ * Any of logp / depth / variance / argmax / quarter / depth_zero may be null.
+ * workspace: dpv_head_ufield_workspace_floats(B, D, H, W) floats, 16-byte aligned.
+ */
+int64_t dpv_head_ufield_workspace_floats(int B, int D, int H, int W);
+int dpv_uf_fused_tables(const int* row_fwd, const int* row_inv, const int* col_fwd,
+                        const int* col_inv, int H, int W, int* row_tab, int* col_tab);
+int dpv_head_ufield(const float* x, const float* d_candi, float* logp, float* depth,
+                    float* variance, int64_t* argmax, float* quarter, const float* intr_up,
+                    const int* row_tab, const int* col_tab, float* uf, float* depth_zero,
+                    float* workspace, int B, int D, int H, int W, int64_t intr_bstride, int in_mode,
+                    float zstart, float zend, float maxd, float mind, float pad_depth, void* stream);
+
 /* ---- K2b : local correlation ------------------------------------------------------------
  * Replaces correlation_cuda.forward (models/correlation_package/correlation_cuda.cc:10-87,
  * kernel correlation_cuda_kernel.cu:41-114) and models/correlation_native.py:13-23 for

@@ -250,6 +250,10 @@ __global__ void __launch_bounds__(HEAD_NT) head_generic_kernel(const HeadArgs a)
     if (a.argmax != nullptr) a.argmax[pix] = (long long)best_k;
 }
 
+// dpv_head_stream.cu: persistent 128-bit streaming kernel (D in {32,64,128}, W % 4 == 0, no addend)
+int launch_head_stream_plain(const HeadArgs& a, cudaStream_t st);
+
+static const int g_head_stream = [] { const char* e = getenv("DPV_HEAD_STREAM"); return e ? atoi(e) : 1; }();
 static const int g_head_t = [] { const char* e = getenv("DPV_HEAD_T"); return e ? atoi(e) : 0; }();
 
 template <int D, int T>
@@ -303,6 +307,10 @@ extern "C" int dpv_head(const float* x, const float* addend, const float* d_cand
     a.B = B; a.D = D; a.H = H; a.W = W; a.mode = in_mode;
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
+    if (g_head_stream) {   // streaming kernel when the shape allows it, else the scalar kernels below
+        const int rc = launch_head_stream_plain(a, st);
+        if (rc != DPV_E_UNSUPP) return rc;
+    }
     switch (D) {
         case 16: return launch_head<16>(a, st);
         case 32: return launch_head<32>(a, st);

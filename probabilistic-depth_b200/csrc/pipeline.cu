@@ -9,6 +9,7 @@
 // item by item, so that the H2D copy of item i+1, the kernels of item i and the D2H copy of
 // item i-1 overlap.  The refined log-DPV stays resident on the device (it is the next frame's
 // feedback input, trainer/default_trainer.py:221-222); only the per-frame products travel back.
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -27,6 +28,9 @@ struct dpv_pipeline {
     long long* argmax;
     int64_t ws_floats_per_item;
     int64_t h2d, d2h;
+    // fused head + UF (dpv_head_ufield): device tables and their host staging copies
+    int *row_tab, *col_tab;
+    std::vector<int> h_row_tab, h_col_tab;
 };
 
 namespace {
@@ -84,7 +88,12 @@ extern "C" int dpv_pipeline_create(dpv_pipeline** out, int device, int B, int V,
     PIPE_TRY(dalloc(&p->uf, (int64_t)B * D * W));
     PIPE_TRY(dalloc(&p->dz, (int64_t)B * HW));
     PIPE_TRY(dalloc(&p->quarter, (int64_t)B * D * (H / 4) * (W / 4) + 1));
-    p->ws_floats_per_item = dpv_ufield_workspace_floats(1, D, H, W);
+    p->ws_floats_per_item = std::max(dpv_ufield_workspace_floats(1, D, H, W),
+                                     (dpv_head_ufield_workspace_floats(1, D, H, W) + 3) & ~(int64_t)3);
+    PIPE_TRY(dalloc(&p->row_tab, (int64_t)H * 4));
+    PIPE_TRY(dalloc(&p->col_tab, W));
+    p->h_row_tab.resize((size_t)H * 4);
+    p->h_col_tab.resize(W);
     PIPE_TRY(dalloc(&p->ws, p->ws_floats_per_item * B));
     *out = p;
     return 0;
@@ -96,7 +105,7 @@ extern "C" int dpv_pipeline_destroy(dpv_pipeline* p) {
     cudaStreamSynchronize(p->s_in); cudaStreamSynchronize(p->s_run); cudaStreamSynchronize(p->s_out);
     void* bufs[] = {p->feats, p->poses, p->K, p->rays, p->d, p->logits, p->intr, p->row_fwd,
                     p->row_inv, p->col_fwd, p->col_inv, p->cost, p->bv, p->refined, p->depth, p->var,
-                    p->argmax, p->uf, p->dz, p->quarter, p->ws};
+                    p->argmax, p->uf, p->dz, p->quarter, p->ws, p->row_tab, p->col_tab};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto e : p->e_in) cudaEventDestroy(e);
     for (auto e : p->e_done) cudaEventDestroy(e);
@@ -136,6 +145,15 @@ extern "C" int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float
     PIPE_TRY(up(p->intr, intr_up, (int64_t)B * 9 * 4));
     PIPE_TRY(up(p->row_fwd, row_fwd, (int64_t)H * 4)); PIPE_TRY(up(p->row_inv, row_inv, (int64_t)H * 4));
     PIPE_TRY(up(p->col_fwd, col_fwd, (int64_t)W * 4)); PIPE_TRY(up(p->col_inv, col_inv, (int64_t)W * 4));
+    // K3 + K5 in one pass when the shifts allow it (they do for the reference's row shifts)
+    const bool fused = (W % 4 == 0) && dpv_head_ufield_workspace_floats(1, D, H, W) > 0 &&
+                       dpv_uf_fused_tables(row_fwd, row_inv, col_fwd, col_inv, H, W,
+                                           p->h_row_tab.data(), p->h_col_tab.data()) == 0;
+    if (fused) {
+        // pageable staging owned by the handle; stream-ordered before the first kernel that reads it
+        PIPE_TRY(up(p->row_tab, p->h_row_tab.data(), (int64_t)H * 16));
+        PIPE_TRY(up(p->col_tab, p->h_col_tab.data(), (int64_t)W * 4));
+    }
     // sum of the bins = E[d] of a zero-padded log-DPV column (see dpv_ufield)
     float pad_depth = 0.f;
     for (int k = 0; k < D; ++k) pad_depth += d_candi[k];
@@ -155,6 +173,14 @@ extern "C" int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float
         PIPE_RC(dpv_head(p->cost + (int64_t)i * D * hw, nullptr, p->d, p->bv + (int64_t)i * D * hw,
                          nullptr, nullptr, nullptr, nullptr, nullptr, 1, D, h, w, DPV_IN_LOGITS,
                          p->s_run));
+        if (fused)
+            PIPE_RC(dpv_head_ufield(p->logits + i * D * HW, p->d, p->refined + i * D * HW,
+                                    p->depth + i * HW, p->var + i * HW, (int64_t*)(p->argmax + i * HW),
+                                    p->quarter + i * D * q4, p->intr + i * 9, p->row_tab, p->col_tab,
+                                    p->uf + (int64_t)i * D * W, p->dz + i * HW,
+                                    p->ws + i * p->ws_floats_per_item, 1, D, H, W, 0, DPV_IN_LOGITS,
+                                    0.6f, 0.6f + 0.3f, 100.f, 0.f, pad_depth, p->s_run));
+        else {
         PIPE_RC(dpv_head(p->logits + i * D * HW, nullptr, p->d, p->refined + i * D * HW, nullptr,
                          p->depth + i * HW, p->var + i * HW, (int64_t*)(p->argmax + i * HW),
                          p->quarter + i * D * q4, 1, D, H, W, DPV_IN_LOGITS, p->s_run));
@@ -162,6 +188,7 @@ extern "C" int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float
                            p->row_fwd, p->row_inv, p->col_fwd, p->col_inv, p->uf + (int64_t)i * D * W,
                            p->dz + i * HW, p->ws + i * p->ws_floats_per_item, 1, D, H, W, 0,
                            DPV_IN_LOGPROB, 0.6f, 0.6f + 0.3f, 100.f, 0.f, pad_depth, p->s_run));
+        }
         PIPE_TRY(cudaEventRecord(p->e_done[i], p->s_run));
         PIPE_TRY(cudaStreamWaitEvent(p->s_out, p->e_done[i], 0));
         if (bv) PIPE_TRY(down(bv + (int64_t)i * D * hw, p->bv + (int64_t)i * D * hw, (int64_t)D * hw * 4));

@@ -18,7 +18,8 @@ from . import _lib, ops
 
 
 class FrameStep:
-    def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None):
+    def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None,
+                 fuse_uf=True):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dev = dev
         self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W = B, V, C, D, h, w, H, W
@@ -37,7 +38,11 @@ class FrameStep:
         self.uf = e(B, D, W)
         self.dz = e(B, H, W)
         self.lib = _lib.load()
-        self.ws = e(int(self.lib.dpv_ufield_workspace_floats(B, D, H, W)))
+        # K3 + K5 in one pass when the shape allows it, else dpv_head followed by dpv_ufield
+        self.tabs = ops.uf_fused_tables(H, W, ops.KITTI_UF["pshift"], dev) if fuse_uf else None
+        nfused = int(self.lib.dpv_head_ufield_workspace_floats(B, D, H, W)) if self.tabs else 0
+        self.fused_uf = nfused > 0
+        self.ws = e(nfused if self.fused_uf else int(self.lib.dpv_ufield_workspace_floats(B, D, H, W)))
         self.luts = ops.shift_luts(H, W, ops.KITTI_UF["pshift"], dev)
         if mode == "upsample":
             self.fused = e(B, D, h, w)
@@ -78,6 +83,15 @@ class FrameStep:
                                     None, None, None, B, D, h, w, ops.IN_LOGITS, st))
         if head_hook is not None:
             head_hook(0)
+        if self.fused_uf:
+            _lib.check(lib.dpv_head_ufield(p(logits_full), p(self.d), p(self.refined), p(self.depth),
+                                           p(self.var), p(self.argmax), p(self.quarter), p(intr_up),
+                                           p(self.tabs[0]), p(self.tabs[1]), p(self.uf), p(self.dz),
+                                           p(self.ws), B, D, H, W, 9, ops.IN_LOGITS, *self.uf_params,
+                                           self.pad_depth, st))
+            if head_hook is not None:
+                head_hook(1)
+            return
         _lib.check(lib.dpv_head(p(logits_full), None, p(self.d), p(self.refined), None, p(self.depth),
                                 p(self.var), p(self.argmax), p(self.quarter), B, D, H, W,
                                 ops.IN_LOGITS, st))
@@ -89,7 +103,8 @@ class FrameStep:
                                   B, D, H, W, 9, ops.IN_LOGPROB, *self.uf_params, self.pad_depth, st))
 
     def launches_per_step(self):
-        return {"default": 5, "upsample": 6, "feedback": 7}[self.mode]
+        n = {"default": 5, "upsample": 6, "feedback": 7}[self.mode]
+        return n - 1 if self.fused_uf else n     # head + UF partial/finish: 3 launches -> 2
 
     # -- algorithmic bytes, per step ---------------------------------
     def algorithmic_bytes(self):
@@ -107,3 +122,15 @@ class FrameStep:
             k["warp_feature"] = 8 * hw * D * (V + 1) + 12 * hw
             k["feedback_fuse"] = 12 * hw * D
         return {n: v * B for n, v in k.items()}
+
+    def dominant_kernel(self):
+        """(name, algorithmic bytes per launch) of the kernel the roofline is quoted on: the
+        full-resolution head.  Fused with the UF it reads the logits once and additionally writes
+        UF [B,D,W] and depth_zero [B,H,W]; it does not re-read the DPV, so K5's 4*HW*D is not
+        counted for it."""
+        B, D, HW = self.B, self.D, self.H * self.W
+        head = 8 * HW * D + 16 * HW
+        if self.fused_uf:
+            return "dpv::head_vec_kernel<4,LOGITS,...,UF> (full-res head + UF, fused)", \
+                B * (head + 4 * D * self.W + 4 * HW)
+        return "dpv::head_vec_kernel<4,LOGITS> (full-res head)", B * head

@@ -333,6 +333,84 @@ def ufield(dpv, d_candi, intr_up, mode="logprob", mask=None, depth=None, params=
     return uf, dz
 
 
+_tab_cache = {}
+
+
+def uf_fused_tables(H, W, pshift, device):
+    """Device tables of the fused head + UF kernel (dpv_uf_fused_tables) for one image shape, or
+    None when the reference's shifts do not compose to "same pixel or padding" for it."""
+    key = (H, W, int(pshift), str(device))
+    if key in _tab_cache:
+        return _tab_cache[key]
+    luts = [t.cpu().numpy().astype(np.int32).copy() for t in shift_luts(H, W, pshift, "cpu")]
+    row_tab = np.zeros((H, 4), dtype=np.int32)
+    col_tab = np.zeros((W,), dtype=np.int32)
+    rc = _lib.load().dpv_uf_fused_tables(luts[0].ctypes.data, luts[1].ctypes.data, luts[2].ctypes.data,
+                                         luts[3].ctypes.data, H, W, row_tab.ctypes.data,
+                                         col_tab.ctypes.data)
+    if rc == -2:
+        tabs = None
+    else:
+        _lib.check(rc)
+        tabs = (torch.from_numpy(row_tab).to(device), torch.from_numpy(col_tab).to(device))
+    _tab_cache[key] = tabs
+    return tabs
+
+
+def head_ufield(x, d_candi, intr_up, mode="logits", logp=True, depth=True, variance=False,
+                argmax=False, quarter=False, params=None):
+    """Depth-bin head and uncertainty field in ONE pass over x [B,D,H,W] (dpv_head_ufield).
+
+    What the reference does back to back on the refined DPV (models/models.py:351 ->
+    trainer/default_trainer.py:221-244,333-336 -> utils/img_utils.py:268-358).  `mode` is
+    "logits" or "logprob"; no ground-truth mask (use `ufield` for that).  Falls back to
+    head() + ufield() -- still our kernels -- for shapes the fused kernel does not take.
+    Returns the dict of head() plus "uf" [B,D,W] and "depth_zero" [B,H,W].
+    """
+    _need(x, "x")
+    x = x.contiguous()
+    B, D, H, W = x.shape
+    p = dict(KITTI_UF if params is None else params)
+    d = depth_bins(d_candi, x.device)
+    if d.numel() != D:
+        raise ValueError("d_candi has %d bins, x has %d" % (d.numel(), D))
+    lib = _lib.load()
+    nws = int(lib.dpv_head_ufield_workspace_floats(B, D, H, W))
+    tabs = uf_fused_tables(H, W, p["pshift"], x.device) if (nws > 0 and W % 4 == 0) else None
+    if tabs is None or mode == "prob":
+        out = head(x, d, mode=mode, logp=True, depth=True, variance=variance, argmax=argmax,
+                   quarter=quarter)
+        out["uf"], out["depth_zero"] = ufield(out["logp"] if mode != "prob" else x, d, intr_up,
+                                              mode="prob" if mode == "prob" else "logprob",
+                                              depth=out["depth"], params=p)
+        return out
+    intr_up, i_bs = _per_item(_need(intr_up, "intr_up"), B, (3, 3), "intr_up")
+    dev = x.device
+    e = lambda shape, dt=torch.float32: torch.empty(shape, device=dev, dtype=dt)
+    out = {}
+    if logp:
+        out["logp"] = torch.empty_like(x)
+    if depth:
+        out["depth"] = e((B, H, W))
+    if variance:
+        out["variance"] = e((B, H, W))
+    if argmax:
+        out["argmax"] = e((B, H, W), torch.int64)
+    if quarter:
+        out["quarter"] = e((B, D, H // 4, W // 4))
+    out["uf"] = e((B, D, W))
+    out["depth_zero"] = e((B, H, W))
+    ws = e((nws,))
+    pad_depth = _bin_sum(d) if mode != "prob" else 0.0
+    f32 = lambda v: float(np.float32(v))
+    _lib.check(lib.dpv_head_ufield(
+        _p(x), _p(d), _p(out.get("logp")), _p(out.get("depth")), _p(out.get("variance")),
+        _p(out.get("argmax")), _p(out.get("quarter")), _p(intr_up), _p(tabs[0]), _p(tabs[1]),
+        _p(out["uf"]), _p(out["depth_zero"]), _p(ws), B, D, H, W, i_bs, _MODE[mode],
+        f32(p["zstart"]), f32(p["zend"]), f32(p["maxd"]), f32(p["mind"]), pad_depth, _stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------- K2b
 def correlation(x1, x2, max_displacement=4):
     """Local correlation [B,(2r+1)^2,H,W] (reference models/correlation_native.py:13-23)."""

@@ -265,6 +265,55 @@ def test_ufield(dpv, golden, name):
     np.testing.assert_allclose(dz.cpu().numpy()[:, :, keep], want_dz[:, :, keep], rtol=1e-4, atol=0)
 
 
+@pytest.mark.parametrize("name", ["small_log", "full_log"])
+def test_head_ufield_fused_vs_golden(dpv, golden, name):
+    """K3 + K5 in one pass (dpv_head_ufield) against the reference's gen_ufield output."""
+    g = golden("ufield")
+    c = cases.ufield_case(name)
+    x = cu(c["logits"])
+    out = dpv.ops.head_ufield(x, c["d_candi"], cu(c["intr_up"]), mode="logits", logp=True, depth=True,
+                              variance=True, argmax=True, quarter=True)
+    plain = dpv.ops.head(x, c["d_candi"], logp=True, depth=True, variance=True, argmax=True, quarter=True)
+    for k in ("logp", "depth", "variance", "argmax", "quarter"):
+        assert torch.equal(out[k], plain[k]), k
+    want_uf, want_dz = g[name + "_uf"], g[name + "_depthzero"]
+    keep = ~_near_threshold_columns(c, True)
+    assert keep.mean() > 0.9
+    uf = out["uf"].cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(uf[:, :, keep]), np.isnan(want_uf[:, :, keep]))
+    np.testing.assert_allclose(uf[:, :, keep], want_uf[:, :, keep], rtol=1e-4, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(out["depth_zero"].cpu().numpy()[:, :, keep], want_dz[:, :, keep], rtol=1e-4, atol=0)
+    # the two-kernel path (dpv_head + dpv_ufield) takes the same per-pixel decisions: same NaN
+    # pattern and depth_zero everywhere, UF equal up to the summation order
+    uf2, dz2 = dpv.ops.ufield(plain["logp"], c["d_candi"], cu(c["intr_up"]), depth=plain["depth"])
+    assert torch.equal(out["depth_zero"], dz2)
+    assert torch.equal(torch.isnan(out["uf"]), torch.isnan(uf2))
+    ok = ~torch.isnan(uf2)
+    assert float(((out["uf"][ok] - uf2[ok]).abs() / uf2[ok].abs().clamp_min(1e-6)).max()) < 1e-5
+    # log-probability input gives the same field as logits input
+    again = dpv.ops.head_ufield(plain["logp"], c["d_candi"], cu(c["intr_up"]), mode="logprob", logp=False)
+    assert torch.equal(torch.isnan(again["uf"]), torch.isnan(out["uf"]))
+
+
+def test_head_ufield_batched_full_size(dpv):
+    """BASELINE size (B=8, 256x384): fused == two-kernel path per item, bit-reproducible run to run."""
+    B, D, H, W = 8, 64, 256, 384
+    s = dpv.synth
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(W // 4, H // 4, B)
+    x = cu(s.ground_plane_logits(7, B, H, W, d, cam["intrinsics_up"][0]))
+    Ku = cu(cam["intrinsics_up"])
+    a = dpv.ops.head_ufield(x, d, Ku, logp=True, depth=True)
+    b = dpv.ops.head_ufield(x, d, Ku, logp=True, depth=True)
+    assert torch.equal(a["uf"].view(torch.int32), b["uf"].view(torch.int32))
+    uf2, dz2 = dpv.ops.ufield(a["logp"], d, Ku, depth=a["depth"])
+    assert torch.equal(a["depth_zero"], dz2)
+    assert torch.equal(torch.isnan(a["uf"]), torch.isnan(uf2))
+    ok = ~torch.isnan(uf2)
+    assert ok.float().mean() > 0.5
+    assert float(((a["uf"][ok] - uf2[ok]).abs() / uf2[ok].abs().clamp_min(1e-6)).max()) < 1e-5
+
+
 # ------------------------------------------------------------------------- K2b
 @pytest.mark.parametrize("name", cases.CORR_CASES)
 def test_correlation(dpv, golden, name):
@@ -328,6 +377,9 @@ def test_host_pipeline_matches_ops(dpv):
     assert torch.equal(out["variance"], hd["variance"].cpu())
     assert torch.equal(out["argmax"], hd["argmax"].cpu())
     assert torch.equal(out["quarter"], hd["quarter"].cpu())
-    np.testing.assert_array_equal(out["uf"].numpy(), uf.cpu().numpy())
+    # the pipeline runs head + UF fused, item by item: same per-pixel decisions, and a UF equal up
+    # to the order in which the rows of a column are added
+    assert torch.equal(torch.isnan(out["uf"]), torch.isnan(uf.cpu()))
+    np.testing.assert_allclose(out["uf"].numpy(), uf.cpu().numpy(), rtol=1e-5, atol=1e-30, equal_nan=True)
     assert torch.equal(out["depth_zero"], dz.cpu())
     pipe.close()

@@ -106,3 +106,30 @@ def test_mirror_modules_keep_the_reference_names(dpv):
     np.testing.assert_array_equal(u.powerf(5.0, 40.0, 64, 1.0), dpv.synth.depth_candidates())
     c = dpv.models.correlation_native.Correlation(max_displacement=4)
     assert c.output_dim == 9 and c.pad_size == 4
+
+
+@pytest.mark.parametrize("H,W", [(256, 384), (64, 96), (384, 1280)])
+def test_fused_uf_tables_match_the_closed_form(dpv, H, W):
+    """dpv_uf_fused_tables (host helper, no device work) on the reference's +/-5-row shifts gives
+    the closed form SURVEY.md 8c verified against gen_ufield: numerator rows y <= H-7 test shifted
+    row y+5, denominator source rows y <= H-6, column W-1 excluded everywhere."""
+    import ctypes
+    luts = [t.numpy().astype(np.int32).copy() for t in dpv.ops.shift_luts(H, W, 5, "cpu")]
+    row_tab = np.zeros((H, 4), dtype=np.int32)
+    col_tab = np.zeros((W,), dtype=np.int32)
+    rc = dpv._lib.load().dpv_uf_fused_tables(*[a.ctypes.data for a in luts], H, W,
+                                             row_tab.ctypes.data, col_tab.ctypes.data)
+    assert rc == 0
+    y = np.arange(H)
+    np.testing.assert_array_equal(row_tab[:, 0], np.where(y <= H - 7, y + 5, -1))
+    np.testing.assert_array_equal(row_tab[:, 1], 0)
+    np.testing.assert_array_equal(row_tab[:, 2], np.where(y <= H - 6, y + 5, -1))
+    np.testing.assert_array_equal(row_tab[:, 3], (y < 5).astype(np.int32))
+    np.testing.assert_array_equal(col_tab[:-1], 1 | 4)
+    assert col_tab[-1] == 8
+    # shifts that do not compose to "same pixel or padding" are refused, not mis-handled
+    bad = [a.copy() for a in luts]
+    bad[1][:] = np.clip(np.arange(H) + 4, 0, H - 1)
+    rc = dpv._lib.load().dpv_uf_fused_tables(*[a.ctypes.data for a in bad], H, W,
+                                             row_tab.ctypes.data, col_tab.ctypes.data)
+    assert rc == -2

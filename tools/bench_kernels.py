@@ -88,6 +88,15 @@ def main():
         f = lambda i: ops.ufield(lps[i], d, Ku)
         med, best = timeit(f, nrot)
         res["ufield_standalone"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        lgs = [lg.clone() for _ in range(nrot)]
+        f = lambda i: ops.head_ufield(lgs[i], d, Ku, logp=True, depth=True, variance=True, argmax=True, quarter=True)
+        med, best = timeit(f, nrot)
+        byt = B * (8 * H * W * D + 16 * H * W + 4 * D * W + 4 * H * W)
+        res["head_full_uf_fused"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        f = lambda i: ops.head(lgs[i], d, logp=True, depth=True, variance=True, argmax=True, quarter=True)
+        med, best = timeit(f, nrot)
+        byt = B * (8 * H * W * D + 16 * H * W)
+        res["head_full_groundplane"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
     if want("fuse"):
         bv = [torch.log_softmax(torch.randn((B, D, h, w), device="cuda"), 1) for _ in range(nrot)]
         dm, mk = s.sparse_depth(3, B, h, w)
