@@ -195,7 +195,7 @@ def run_ours(args, dpv):
     B = WL["B"]
     hi = host_inputs(dpv, B, seed=rank)
     step = frame_mod.FrameStep(B, WL["V"], WL["C"], WL["D"], WL["h"], WL["w"], WL["H"], WL["W"], hi["d"],
-                               sigma=10.0, mode="default", device=dev)
+                               sigma=10.0, mode="default", device=dev, fuse_uf=args.fuse_uf)
     # two input sets in HBM, alternated: 2 x 227 MB read + 227 MB written per step >> 126 MB L2
     nset = 2
     dsets = []
@@ -313,6 +313,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fuse-uf", action="store_true",
+                    help="run K3+K5 as the single fused TMA-fed kernel instead of dpv_head + dpv_ufield")
     args = ap.parse_args()
     dpv = importlib.import_module("probabilistic-depth_b200")
     if args.impl == "reference":

@@ -65,7 +65,10 @@ __device__ __forceinline__ int group_min(int v) {
 // maximum of the log-probabilities, what torch.argmax returns on this kernel's own output) is the
 // first bin whose log p equals -ln S.  (A running "best so far" chain makes the compiler keep
 // every log p live: +100 registers.)  NaN inputs are not supported.
-template <int D, int T, int MODE, bool ADD>
+// LOGP / PROB / QTR say which per-element outputs exist: a store that is merely predicated off still
+// costs its issue slot and its address arithmetic (ncu on the first version: three predicated
+// stores per element, 43 % of all instructions were LEA/IMAD/IADD3).
+template <int D, int T, int MODE, bool ADD, bool LOGP, bool PROB, bool QTR>
 __global__ void __launch_bounds__(HEAD_NT) head_kernel(const HeadArgs a) {
     constexpr int DT = D / T;          // bins per thread
     constexpr int PIX = HEAD_NT / T;   // pixels per CTA
@@ -137,16 +140,18 @@ __global__ void __launch_bounds__(HEAD_NT) head_kernel(const HeadArgs a) {
     // 1/4-resolution hand-off: is this pixel kept, and where does it go
     const int h4 = a.H / 4, w4 = a.W / 4;
     bool q_keep = false;
-    long long qoff = 0;
-    if (a.quarter != nullptr) {
+    float* qp = nullptr;
+    if (QTR) {
         const int y = q / a.W, xx = q - y * a.W;
         q_keep = live && ((y & 3) == 0) && ((xx & 3) == 0) && ((y >> 2) < h4) && ((xx >> 2) < w4);
-        qoff = ((long long)b * D + kb + (DT - 1)) * h4 * w4 + (y >> 2) * w4 + (xx >> 2);
+        qp = a.quarter + ((long long)b * D + kb + (DT - 1)) * h4 * w4 + (q_keep ? (y >> 2) * w4 + (xx >> 2) : 0);
     }
+    const int q4 = h4 * w4;
 
     // Main pass, last bin first so that the smallest index among equal maxima is what remains.
-    const bool has_logp = (a.logp != nullptr) && live, has_prob = (a.prob != nullptr) && live;
-    long long off = base + (long long)(DT - 1) * HW;
+    // One running pointer per output (a single 64-bit add per bin).
+    float* lp_ptr = LOGP ? a.logp + base + (long long)(DT - 1) * HW : nullptr;
+    float* pr_ptr = PROB ? a.prob + base + (long long)(DT - 1) * HW : nullptr;
     float mean = 0.f;
     int best_k = 1 << 30;
 #pragma unroll
@@ -167,13 +172,20 @@ __global__ void __launch_bounds__(HEAD_NT) head_kernel(const HeadArgs a) {
         best_k = (lp == top) ? (kb + k) : best_k;
         mean = fmaf(dk, pr, mean);
         v[k] = pr;
-        if (has_logp) st_stream(a.logp + off, (MODE == DPV_IN_PROB) ? logf(pr) : lp);
-        if (has_prob) st_stream(a.prob + off, pr);
-        off -= HW;
-        asm volatile("" : "+l"(off));
-        if (q_keep) {
-            a.quarter[qoff] = (MODE == DPV_IN_PROB) ? pr : lp;
-            qoff -= h4 * w4;
+        if (LOGP) {
+            if (live) st_stream(lp_ptr, (MODE == DPV_IN_PROB) ? logf(pr) : lp);
+            lp_ptr -= HW;
+            asm volatile("" : "+l"(lp_ptr));
+        }
+        if (PROB) {
+            if (live) st_stream(pr_ptr, pr);
+            pr_ptr -= HW;
+            asm volatile("" : "+l"(pr_ptr));
+        }
+        if (QTR) {
+            if (q_keep) *qp = (MODE == DPV_IN_PROB) ? pr : lp;
+            qp -= q4;
+            asm volatile("" : "+l"(qp));
         }
     }
     mean = group_sum<T>(mean);
@@ -250,10 +262,13 @@ __global__ void __launch_bounds__(HEAD_NT) head_generic_kernel(const HeadArgs a)
     if (a.argmax != nullptr) a.argmax[pix] = (long long)best_k;
 }
 
-// dpv_head_stream.cu: persistent 128-bit streaming kernel (D in {32,64,128}, W % 4 == 0, no addend)
+// dpv_head_stream.cu: persistent TMA-fed kernel (D <= 64, W % 4 == 0, no addend / prob output).  It
+// is what dpv_head_ufield runs; for the plain head the short-CTA kernel below is faster at the
+// model's sizes (measured, profiles/README.md: a persistent CTA gets only ~8 rows each at
+// 8 x 256 x 384, so its prologue, tail and 8-vs-9-row imbalance cost ~15 %), so it is opt-in here.
 int launch_head_stream_plain(const HeadArgs& a, cudaStream_t st);
 
-static const int g_head_stream = [] { const char* e = getenv("DPV_HEAD_STREAM"); return e ? atoi(e) : 1; }();
+static const int g_head_stream = [] { const char* e = getenv("DPV_HEAD_STREAM"); return e ? atoi(e) : 0; }();
 static const int g_head_t = [] { const char* e = getenv("DPV_HEAD_T"); return e ? atoi(e) : 0; }();
 
 template <int D, int T>
@@ -261,10 +276,24 @@ static int launch_head_t(const HeadArgs& a, cudaStream_t st) {
     const int HW = a.H * a.W;
     constexpr int PIX = HEAD_NT / T;
     dim3 grid((HW + PIX - 1) / PIX, a.B), block(HEAD_NT);
-    if (a.mode == DPV_IN_LOGITS && a.addend) head_kernel<D, T, DPV_IN_LOGITS, true><<<grid, block, 0, st>>>(a);
-    else if (a.mode == DPV_IN_LOGITS) head_kernel<D, T, DPV_IN_LOGITS, false><<<grid, block, 0, st>>>(a);
-    else if (a.mode == DPV_IN_LOGPROB) head_kernel<D, T, DPV_IN_LOGPROB, false><<<grid, block, 0, st>>>(a);
-    else head_kernel<D, T, DPV_IN_PROB, false><<<grid, block, 0, st>>>(a);
+    const bool lp = a.logp != nullptr, pr = a.prob != nullptr, qt = a.quarter != nullptr;
+    // the output combinations the callers use; anything else takes head_generic_kernel
+    const int combo = (lp && !pr && !qt) ? 0 : (lp && !pr && qt) ? 1 : (lp && pr && !qt) ? 2 :
+                      (!lp && !pr && !qt) ? 3 : (lp && pr && qt) ? 4 : -1;
+    if (combo < 0) return DPV_E_UNSUPP;
+#define DPV_HEAD_GO(MODE_, ADD_)                                                                            \
+    do {                                                                                                    \
+        if (combo == 0) head_kernel<D, T, MODE_, ADD_, true, false, false><<<grid, block, 0, st>>>(a);      \
+        else if (combo == 1) head_kernel<D, T, MODE_, ADD_, true, false, true><<<grid, block, 0, st>>>(a);  \
+        else if (combo == 2) head_kernel<D, T, MODE_, ADD_, true, true, false><<<grid, block, 0, st>>>(a);  \
+        else if (combo == 3) head_kernel<D, T, MODE_, ADD_, false, false, false><<<grid, block, 0, st>>>(a); \
+        else head_kernel<D, T, MODE_, ADD_, true, true, true><<<grid, block, 0, st>>>(a);                   \
+    } while (0)
+    if (a.mode == DPV_IN_LOGITS && a.addend) DPV_HEAD_GO(DPV_IN_LOGITS, true);
+    else if (a.mode == DPV_IN_LOGITS) DPV_HEAD_GO(DPV_IN_LOGITS, false);
+    else if (a.mode == DPV_IN_LOGPROB) DPV_HEAD_GO(DPV_IN_LOGPROB, false);
+    else DPV_HEAD_GO(DPV_IN_PROB, false);
+#undef DPV_HEAD_GO
     DPV_LAUNCH_END();
     return 0;
 }
@@ -311,14 +340,16 @@ extern "C" int dpv_head(const float* x, const float* addend, const float* d_cand
         const int rc = launch_head_stream_plain(a, st);
         if (rc != DPV_E_UNSUPP) return rc;
     }
+    int rc = DPV_E_UNSUPP;
     switch (D) {
-        case 16: return launch_head<16>(a, st);
-        case 32: return launch_head<32>(a, st);
-        case 64: return launch_head<64>(a, st);
-        case 128: return launch_head<128>(a, st);
-        case 256: return launch_head<256>(a, st);
+        case 16: rc = launch_head<16>(a, st); break;
+        case 32: rc = launch_head<32>(a, st); break;
+        case 64: rc = launch_head<64>(a, st); break;
+        case 128: rc = launch_head<128>(a, st); break;
+        case 256: rc = launch_head<256>(a, st); break;
         default: break;
     }
+    if (rc != DPV_E_UNSUPP) return rc;
     dim3 grid((HW + HEAD_NT - 1) / HEAD_NT, B), block(HEAD_NT);
     head_generic_kernel<<<grid, block, 0, st>>>(a);
     DPV_LAUNCH_END();

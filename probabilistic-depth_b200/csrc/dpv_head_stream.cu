@@ -1,31 +1,34 @@
-// K3 (+K5): persistent, bulk-copy staged depth-bin head, optionally fused with the UF collapse.
+// K3 (+K5): persistent, bulk-copy fed depth-bin head, optionally fused with the UF collapse.
 //
 // log-softmax over the bin axis fused with everything the reference derives from it in separate
 // passes (E[d], Var[d], arg-max, the 1/4-resolution hand-off; see dpv_head.cu for the sites).
 // A thread owns ONE image column of a 128-column strip and keeps the D (<= 64) bins of the current
 // pixel in registers: no shuffles, no replicated per-pixel work.  The CTA walks down its run of rows;
-// the grid is sized to the machine and the rows of all strips are split evenly over the CTAs.
+// the grid is sized to the machine (5 CTAs of 4 warps per SM) and the rows of all strips are split
+// evenly over the CTAs.
 //
-// Data movement is done by the bulk-copy engine (cp.async.bulk, the non-tensor TMA path) instead
-// of per-thread loads and stores: one [D][128] tile = D row segments of 512 contiguous bytes, each
-// moved by one instruction of one thread, completion signalled on an mbarrier; two tiles are in
-// flight per CTA (the next row lands while the current one is computed); log p is written back
-// into the tile in place and leaves through cp.async.bulk as well.  The compute threads only see
-// shared memory at compile-time offsets.  Why: ncu on the first two kernels (profiles/) showed
-// 38-43 % of all issued instructions were global address arithmetic (LEA/IADD3/IMAD) and the
-// kernel issue-bound at 73 % issue utilisation, 81 % of the measured HBM roof.
+// The input side is done by the bulk-copy engine (cp.async.bulk, the non-tensor TMA path): one
+// [D][128] tile = D row segments of 512 contiguous bytes, each moved by one instruction issued by
+// one elected lane, completion counted in bytes on an mbarrier.  The compute threads read the tile
+// at compile-time shared-memory offsets, hand the stage back after the arg-max pass over their
+// column, and the next row is in flight during the whole soft-max of the current one (5 CTAs x
+// 32 KB per SM in flight, no registers spent on it).  Why: ncu on the first kernels (profiles/)
+// showed 38-43 % of all issued instructions were global address arithmetic (LEA/IADD3/IMAD), three
+// predicated stores per element, and the kernel issue-bound at 81 % of the measured HBM roof.
 //
 // UF = true additionally performs gen_ufield (reference utils/img_utils.py:268-358) on the
 // probabilities while they are in registers.  The reference's two nearest-neighbour row shifts
 // cancel: for image pixel (y, x) the numerator weight is band(E[d](y, x), shifted row) times border
 // predicates (closed form verified to reproduce gen_ufield exactly, NaN pattern
 // included); the predicates come from the reference's own grid construction through two small
-// tables (dpv_uf_fused_tables).  Each thread accumulates its column over the CTA's run of rows in a
-// column-private shared-memory slot (no barrier, no atomics; rows off the road band cost nothing),
-// the CTA writes one partial record per (run, strip) if any pixel was on the band, and
-// uf_stream_finish_kernel adds the records of a column in run order: bit-reproducible.
+// tables (dpv_uf_fused_tables).  Each thread keeps its column's running sums for the CTA's run of
+// rows in a private slot of the CTA's record (global memory, L2-resident; rows off the road band
+// cost nothing), and uf_stream_finish_kernel adds the records of a column in run order: no
+// atomics, bit-reproducible.
 #include <algorithm>
 #include <cstdlib>
+
+#include <cuda.h>
 
 #include "dpv_common.cuh"
 
@@ -33,6 +36,7 @@ namespace dpv {
 
 constexpr int HS_NT = 128;            // threads per CTA = columns per strip
 constexpr int HS_NW = HS_NT / 32;     // warps per CTA
+constexpr int HS_CTAS_PER_SM = 5;     // 96 registers x 128 threads, 33 KB of shared memory
 
 struct HeadStreamArgs {
     const float* x; const float* d;
@@ -40,12 +44,14 @@ struct HeadStreamArgs {
     // fused uncertainty field
     const int4* row_tab; const int* col_tab; const float* intr;
     float* depth_zero; float* rec; int* flag;
-    int B, H, W, S2, nseg;
-    long long units;                  // B * S2 * H rows of strips
+    int B, H, W, S2, GP;              // S2 strips per row, GP CTAs per (item, strip)
     long long intr_bs, rec_floats;
     float zstart, zend, maxd1, mind, pad_depth;
 };
 
+__device__ __forceinline__ void hs_st(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ float hs_ex2(float t) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
@@ -68,10 +74,13 @@ __device__ __forceinline__ void hs_mbar_wait(unsigned long long* bar, unsigned p
                      "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(hs_smem(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
-// global -> shared, completion counted in bytes on the mbarrier
-__device__ __forceinline__ void hs_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(hs_smem(dst)), "l"(src), "r"(bytes), "r"(hs_smem(bar)) : "memory");
+// TMA tile load: box [D][1][128] of the (x, y, item*D + bin) view of the volume -> shared memory,
+// completion counted in bytes on the mbarrier; columns past W are zero-filled by the engine.
+__device__ __forceinline__ void hs_tma_load(void* dst, const CUtensorMap* map, int x, int y, int kb,
+                                            unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(hs_smem(dst)), "l"(map), "r"(x), "r"(y), "r"(kb), "r"(hs_smem(bar)) : "memory");
 }
 // shared -> global, tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void hs_bulk_s2g(void* dst, const void* src, unsigned bytes) {
@@ -97,17 +106,12 @@ __device__ __forceinline__ float hs_yf(int ys, float fy, float cy) {
     return __fdiv_rn(__fsub_rn((float)ys, cy), fy);
 }
 
-// first unit of CTA c when `units` rows are split over G CTAs (contiguous, sizes differ by <= 1)
-__host__ __device__ __forceinline__ long long hs_first_unit(long long c, long long units, long long G) {
-    return (c * units) / G;
-}
-
-// Second half of a row: log p / p per bin, E[d], arg-max; log p goes back into the tile in place.
-// WITH_Q is CTA-uniform (rows y % 4 == 0 feed the 1/4-resolution hand-off).
+// Second half of a row: log p / p per bin, E[d], arg-max, log p stored.  WITH_Q is CTA-uniform
+// (rows y % 4 == 0 feed the 1/4-resolution hand-off).
 template <int D, int MODE, bool LOGP, bool WITH_Q>
-__device__ __forceinline__ void hs_main_pass(float (&v)[D], const float* d_s, float* tile, float ln_s,
-                                             float log2_s, float top, float* qp, int q4, bool q_keep,
-                                             float& mean_out, int& best_out) {
+__device__ __forceinline__ void hs_main_pass(float (&v)[D], const float* d_s, float* lp_ptr, int HW,
+                                             bool live, float ln_s, float log2_s, float top, float* qp,
+                                             int q4, bool q_keep, float& mean_out, int& best_out) {
     float mean0 = 0.f, mean1 = 0.f;
     int best_k = 1 << 30;
     // last bin first so that the smallest index among equal maxima is what remains
@@ -120,113 +124,86 @@ __device__ __forceinline__ void hs_main_pass(float (&v)[D], const float* d_s, fl
         best_k = (lp == top) ? k : best_k;
         if (kk & 1) mean1 = fmaf(d_s[k], pr, mean1); else mean0 = fmaf(d_s[k], pr, mean0);
         v[k] = pr;
-        if (LOGP && MODE != DPV_IN_LOGPROB) tile[k * HS_NT] = lp;     // immediate-offset STS
+        if (LOGP) {
+            if (live) hs_st(lp_ptr, lp);
+            lp_ptr -= HW;
+            asm volatile("" : "+l"(lp_ptr));     // keep one running pointer (a 64-bit add per bin)
+        }
         if (WITH_Q) {
             if (q_keep) *qp = lp;
             qp -= q4;
+            asm volatile("" : "+l"(qp));
         }
     }
     mean_out = mean0 + mean1;
     best_out = best_k;
 }
 
-// One thread = one image column of a 128-column strip; the CTA walks down its run of rows.  Tiles
-// ([D][128] floats = one row of the strip, all bins) are brought in by cp.async.bulk into a 2-stage
-// ring, transformed in place and written back by cp.async.bulk: the SM's instruction stream has no
-// global address arithmetic at all (the first kernels spent 38-43 % of their issue slots on it).
+// One thread = one image column of a 128-column strip; the CTA walks down its run of rows.  The
+// input tile ([D][128] floats = one row of the strip, all bins) is brought into shared memory by
+// cp.async.bulk (completion on an mbarrier), copied to registers with compile-time-offset LDS, and
+// the stage is handed straight back to the copy engine for the next row, which is then in flight
+// for the whole soft-max of the current one.  log p leaves through coalesced 128-byte STGs.
 template <int D, int MODE, bool LOGP, bool UF>
-__global__ void __launch_bounds__(HS_NT) head_stream_kernel(const HeadStreamArgs a) {
-    extern __shared__ __align__(128) unsigned char hs_smem_raw[];
-    float* stage = reinterpret_cast<float*>(hs_smem_raw);                 // [2][D][128]
-    float* acc_s = stage + 2 * D * HS_NT;                                 // [D][128] (UF only)
-    float* d_s = acc_s + (UF ? D * HS_NT : 0);                            // [D]
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(d_s + D);   // [2]
+__global__ void __launch_bounds__(HS_NT, UF ? HS_CTAS_PER_SM - 1 : HS_CTAS_PER_SM)
+head_stream_kernel(const HeadStreamArgs a, const __grid_constant__ CUtensorMap tmap_x) {
+    __shared__ __align__(128) float stage[D * HS_NT];                     // [D][128]
+    __shared__ float d_s[D];
+    __shared__ __align__(8) unsigned long long full;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int HW = a.H * a.W;
-    const long long u0 = hs_first_unit(blockIdx.x, a.units, gridDim.x);
-    const long long u1 = hs_first_unit(blockIdx.x + 1, a.units, gridDim.x);
+    // CTA -> (item, strip, j): rows j, j + GP, j + 2 GP, ... of one 128-column strip.  The CTAs that
+    // run together therefore stream GP consecutive rows of every strip: contiguous DRAM pages.
+    const int bs = blockIdx.x / a.GP, j = blockIdx.x - bs * a.GP;
+    const int b = bs / a.S2, ws = bs - b * a.S2;
+    const int x0 = ws * HS_NT;
+    const bool live = (x0 + tid) < a.W;
+    const int x = x0 + (live ? tid : 0);         // dead threads shadow column x0 (never stored)
     for (int k = tid; k < D; k += HS_NT) d_s[k] = __ldg(a.d + k);
-    if (UF) {
-#pragma unroll 8
-        for (int k = 0; k < D; ++k) acc_s[k * HS_NT + tid] = 0.f;
-    }
     if (tid == 0) {
-        hs_mbar_init(&full[0], 1);
-        hs_mbar_init(&full[1], 1);
+        hs_mbar_init(&full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (u0 >= u1) return;
+    if (j >= a.H) return;
 
-    long long bs = u0 / a.H;                     // (item, strip)
-    int y = (int)(u0 - bs * a.H);
-    int b = (int)(bs / a.S2);
-    int ws = (int)(bs - (long long)b * a.S2);
-    int x0 = ws * HS_NT;
-    int cw = min(HS_NT, a.W - x0);               // live columns of this strip (multiple of 4)
-    // Bulk copies are uniform-datapath instructions: issuing them from every lane makes the compiler
-    // serialise the warp lane by lane.  Lane 0 of each warp moves D/4 bins' 512-byte row segments.
-    constexpr int KPW = D / HS_NW;               // bins per issuing warp
-    const bool issuer = (lane == 0);
-    const int k_lo = warp * KPW;
-
-    // prologue: first tile into stage 0
-    if (issuer) {
-        if (warp == 0) hs_mbar_expect_tx(&full[0], (unsigned)(D * cw * 4));
-        const float* src = a.x + ((long long)b * D + k_lo) * HW + (long long)y * a.W + x0;
-#pragma unroll 4
-        for (int k = 0; k < KPW; ++k)
-            hs_bulk_g2s(stage + (k_lo + k) * HS_NT, src + (long long)k * HW, (unsigned)(cw * 4), &full[0]);
+    // One TMA request per tile, issued by one elected lane.  (Measured: D separate 512-byte
+    // cp.async.bulk requests per tile cap the copy engine at ~55 % of the HBM rate.)
+    constexpr unsigned kTileBytes = D * HS_NT * 4;
+    if (warp == 0 && lane == 0) {
+        hs_mbar_expect_tx(&full, kTileBytes);
+        hs_tma_load(stage, &tmap_x, x0, j, b * D, &full);
     }
 
     float cnt = 0.f, fy = 0.f, cy = 0.f;
-    bool seg_any = false;
-    int seg = 0, ct = 0;
-    bool live = tid < cw;
+    bool any_band = false, has_acc = false;
+    int ct = 0;
     if (UF) {
         fy = __ldg(a.intr + b * a.intr_bs + 4); cy = __ldg(a.intr + b * a.intr_bs + 5);
-        ct = live ? __ldg(a.col_tab + x0 + tid) : 0;
+        ct = live ? __ldg(a.col_tab + x) : 0;
     }
     const int h4 = a.H / 4, w4 = a.W / 4, q4 = h4 * w4;
+    const long long item = (long long)b * D * HW;
+    float* const rec = UF ? a.rec + (long long)blockIdx.x * a.rec_floats + tid : nullptr;
 
     int it = 0;
-    for (long long u = u0; u < u1; ++u, ++it) {
-        const int s = it & 1;
-        float* tile = stage + s * D * HS_NT + tid;
-        // ---- where is the next row; bring it in ------------------------------------------------
-        const bool has_next = (u + 1 < u1);
-        const bool same_strip = (y + 1 < a.H);
-        int nb = b, nws = ws, ny = y + 1, nx0 = x0, ncw = cw;
-        if (!same_strip) {
-            const long long nbs = bs + 1;
-            nb = (int)(nbs / a.S2);
-            nws = (int)(nbs - (long long)nb * a.S2);
-            ny = 0;
-            nx0 = nws * HS_NT;
-            ncw = min(HS_NT, a.W - nx0);
-        }
-        if (has_next && issuer) {
-            // stage s^1 was written back by this thread's bulk store of the previous tile: wait until
-            // the engine has read it out, then overwrite
-            hs_bulk_wait_read0();
-            if (warp == 0) hs_mbar_expect_tx(&full[s ^ 1], (unsigned)(D * ncw * 4));
-            const float* src = a.x + ((long long)nb * D + k_lo) * HW + (long long)ny * a.W + nx0;
-            float* dst = stage + (s ^ 1) * D * HS_NT + k_lo * HS_NT;
-#pragma unroll 4
-            for (int k = 0; k < KPW; ++k)
-                hs_bulk_g2s(dst + k * HS_NT, src + (long long)k * HW, (unsigned)(ncw * 4), &full[s ^ 1]);
-        }
-
-        // ---- the current tile -------------------------------------------------------------------
-        hs_mbar_wait(&full[s], (unsigned)((it >> 1) & 1));
+    for (int y = j; y < a.H; y += a.GP, ++it) {
+        // ---- the current tile: shared memory -> registers ----------------------------------------
+        hs_mbar_wait(&full, (unsigned)(it & 1));
         float v[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) v[k] = tile[k * HS_NT];              // immediate-offset LDS
+        for (int k = 0; k < D; ++k) v[k] = stage[k * HS_NT + tid];       // immediate-offset LDS
         float ln_s = 0.f, log2_s = 0.f, top;
-        if (MODE == DPV_IN_LOGITS) {
-            float m = v[0];
+        float m = v[0];
 #pragma unroll
-            for (int k = 1; k < D; ++k) m = fmaxf(m, v[k]);
+        for (int k = 1; k < D; ++k) m = fmaxf(m, v[k]);
+        // every thread now holds its column (m depends on all D values): give the stage back
+        __syncthreads();
+        if (y + a.GP < a.H && warp == 0 && lane == 0) {
+            hs_mbar_expect_tx(&full, kTileBytes);
+            hs_tma_load(stage, &tmap_x, x0, y + a.GP, b * D, &full);
+        }
+        if (MODE == DPV_IN_LOGITS) {
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll
             for (int k = 0; k < D; k += 2) {
@@ -237,37 +214,22 @@ __global__ void __launch_bounds__(HS_NT) head_stream_kernel(const HeadStreamArgs
             log2_s = ln_s * kHsL2e;
             top = -ln_s;
         } else {
-            top = v[0];
-#pragma unroll
-            for (int k = 1; k < D; ++k) top = fmaxf(top, v[k]);
+            top = m;
         }
 
-        const int x = x0 + tid;
-        const int pix = y * a.W + (live ? x : x0);
+        const int pix = y * a.W + x;
         float mean;
         int best_k;
+        float* lp_ptr = LOGP ? a.logp + item + (long long)(D - 1) * HW + pix : nullptr;
         const bool want_q = (a.quarter != nullptr) && ((y & 3) == 0) && ((y >> 2) < h4);   // CTA-uniform
         if (want_q) {
             const bool q_keep = live && ((x & 3) == 0) && ((x >> 2) < w4);
-            float* qp = a.quarter + ((long long)b * D + (D - 1)) * q4 + (y >> 2) * w4 + ((live ? x : x0) >> 2);
-            hs_main_pass<D, MODE, LOGP, true>(v, d_s, tile, ln_s, log2_s, top, qp, q4, q_keep, mean, best_k);
+            float* qp = a.quarter + ((long long)b * D + (D - 1)) * q4 + (y >> 2) * w4 + (x >> 2);
+            hs_main_pass<D, MODE, LOGP, true>(v, d_s, lp_ptr, HW, live, ln_s, log2_s, top, qp, q4, q_keep,
+                                              mean, best_k);
         } else {
-            hs_main_pass<D, MODE, LOGP, false>(v, d_s, tile, ln_s, log2_s, top, nullptr, 0, false, mean, best_k);
-        }
-        if (LOGP) {
-            // hand the transformed tile to the bulk-copy engine
-            hs_fence_async();
-            __syncthreads();
-            if (issuer) {
-                float* dst = a.logp + ((long long)b * D + k_lo) * HW + (long long)y * a.W + x0;
-                const float* src = stage + s * D * HS_NT + k_lo * HS_NT;
-#pragma unroll 4
-                for (int k = 0; k < KPW; ++k)
-                    hs_bulk_s2g(dst + (long long)k * HW, src + k * HS_NT, (unsigned)(cw * 4));
-                hs_bulk_commit();
-            }
-        } else {
-            __syncthreads();          // every thread is done reading stage s before it is refilled
+            hs_main_pass<D, MODE, LOGP, false>(v, d_s, lp_ptr, HW, live, ln_s, log2_s, top, nullptr, 0,
+                                               false, mean, best_k);
         }
 
         const long long opix = (long long)b * HW + pix;
@@ -293,73 +255,58 @@ __global__ void __launch_bounds__(HS_NT) head_stream_kernel(const HeadStreamArgs
             const float wn = (live && rt.x >= 0 && (ct & 1)) ? hs_band(a, zn, hs_yf(rt.x, fy, cy)) : 0.f;
             const float wd = (live && rt.z >= 0 && (ct & 4)) ? hs_band(a, mean, hs_yf(rt.z, fy, cy)) : 0.f;
             if (live && a.depth_zero != nullptr) a.depth_zero[opix] = __fmul_rn(mean, wn);
-            const bool mine = (wn != 0.f) | (wd != 0.f);
-            seg_any |= (__any_sync(0xffffffffu, mine) != 0);
+            any_band |= (wn != 0.f) | (wd != 0.f);
+            // The column's running sums live in this CTA's record (global memory, L2-resident, one
+            // private slot per thread and bin): rows off the road band cost nothing, no shared memory
+            // is tied up, and the order of the additions is fixed.
             if (wn != 0.f) {
+                if (has_acc) {
 #pragma unroll
-                for (int k = 0; k < D; ++k)
-                    acc_s[k * HS_NT + tid] = __fadd_rn(acc_s[k * HS_NT + tid], __fmul_rn(v[k], wn));
+                    for (int k0 = 0; k0 < D; k0 += 8) {
+                        float r[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) r[k] = rec[(k0 + k) * HS_NT];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            rec[(k0 + k) * HS_NT] = __fadd_rn(r[k], __fmul_rn(v[k0 + k], wn));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) rec[k * HS_NT] = __fmul_rn(v[k], wn);
+                    has_acc = true;
+                }
             }
             cnt = __fadd_rn(cnt, wd);
-            // ---- end of this segment (run leaves the strip, or ends): write its record --------------
-            if (!has_next || !same_strip) {
-                const long long rid = (long long)blockIdx.x * a.nseg + seg;
-                if (seg_any) {
-                    // record layout: [D][128] partial sums, then [128] counts
-                    float* rec = a.rec + rid * a.rec_floats;
-#pragma unroll 8
-                    for (int k = 0; k < D; ++k) {
-                        rec[k * HS_NT + tid] = acc_s[k * HS_NT + tid];
-                        acc_s[k * HS_NT + tid] = 0.f;
-                    }
-                    rec[D * HS_NT + tid] = cnt;
-                }
-                if (lane == 0) a.flag[rid * HS_NW + warp] = seg_any ? 1 : 0;
-                seg_any = false;
-                cnt = 0.f;
-                ++seg;
-            }
-        }
-
-        // ---- next row ----------------------------------------------------------------------------
-        if (has_next) {
-            if (!same_strip) {
-                bs += 1;
-                live = tid < ncw;
-                if (UF) {
-                    fy = __ldg(a.intr + nb * a.intr_bs + 4); cy = __ldg(a.intr + nb * a.intr_bs + 5);
-                    ct = live ? __ldg(a.col_tab + nx0 + tid) : 0;
-                }
-            }
-            b = nb; ws = nws; y = ny; x0 = nx0; cw = ncw;
         }
     }
-    if (LOGP && issuer) hs_bulk_wait_all();      // shared memory must outlive the last bulk store
+    if (UF) {
+        // record layout: [D][128] sums, then [128] counts; valid when the warp's flag is set
+        const bool warp_any = __any_sync(0xffffffffu, any_band) != 0;
+        if (warp_any) {
+            if (!has_acc) {
+#pragma unroll 8
+                for (int k = 0; k < D; ++k) rec[k * HS_NT] = 0.f;
+            }
+            rec[D * HS_NT] = cnt;
+        }
+        if (lane == 0) a.flag[(long long)blockIdx.x * HS_NW + warp] = warp_any ? 1 : 0;
+    }
 }
 
-// UF[b,k,x] = sum over the runs covering the column of (partial sums) / (counts + padding rows).
-// 0/0 = NaN as in the reference.  block (32 columns, 8 bins); all 32 columns of a block lie in one
-// warp's strip of one wide strip (both are multiples of 32 columns wide or the block is clipped).
-constexpr int HS_FIN_PIECES = 64;
+// UF[b,k,x] = sum over the CTAs of the column's strip (in CTA order) of their partial sums, divided
+// by (their counts + the padding rows' count).  0/0 = NaN as in the reference.  block (32 columns,
+// 8 bins); a 32-column block lies inside one warp's quarter of one strip.
 template <int D>
-__global__ void __launch_bounds__(256) uf_stream_finish_kernel(const HeadStreamArgs a, float* uf, int G) {
-    constexpr int CWW = 32, CWC = HS_NT;
+__global__ void __launch_bounds__(256) uf_stream_finish_kernel(const HeadStreamArgs a, float* uf) {
     __shared__ float den_s[8][32];
-    __shared__ long long rid_s[HS_FIN_PIECES];
-    __shared__ int nflag_s;
+    __shared__ int on_s[64];
     const int c = threadIdx.x, g = threadIdx.y, tid = g * 32 + c;
     const int x = blockIdx.x * 32 + c, b = blockIdx.z;
     const int k = blockIdx.y * 8 + g;
     const bool ok = x < a.W;
     const int xe = ok ? x : 0;
-    const int ws = xe / CWC, xin = xe - ws * CWC, wq = xin / CWW;
-    // pieces are per strip; a 32-column block never straddles two 128-column strips
-    const int ws0 = (blockIdx.x * 32) / CWC;
-    const long long bs = (long long)b * a.S2 + ws0;
-    const long long ufirst = bs * a.H, ulast = ufirst + a.H - 1;
-    // CTA whose run holds unit u: the largest c with floor(c * units / G) <= u
-    const int c_lo = (int)(((ufirst + 1) * G + a.units - 1) / a.units - 1);
-    const int c_hi = (int)(((ulast + 1) * G + a.units - 1) / a.units - 1);
+    const int ws = (blockIdx.x * 32) / HS_NT, xin = xe - ws * HS_NT, wq = (blockIdx.x * 32 - ws * HS_NT) / 32;
+    const long long cta0 = ((long long)b * a.S2 + ws) * a.GP;
     const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
     // shifted-frame pixels that sample the zero padding (their E[d] is pad_depth): rows split over g
     float den = 0.f;
@@ -369,42 +316,27 @@ __global__ void __launch_bounds__(256) uf_stream_finish_kernel(const HeadStreamA
             if (colpad || __ldg(a.row_tab + ys).w) den += hs_band(a, a.pad_depth, hs_yf(ys, fy, cy));   // small integers: exact
     }
     float num = 0.f;
-    for (int p0 = c_lo; p0 <= c_hi; p0 += HS_FIN_PIECES) {
-        const int np = min(HS_FIN_PIECES, c_hi - p0 + 1);
+    for (int p0 = 0; p0 < a.GP; p0 += 64) {
+        const int np = min(64, a.GP - p0);
         __syncthreads();
-        if (tid == 0) nflag_s = 0;
+        // flags are per (CTA, warp): uniform over this block's 32 columns
+        if (tid < np) on_s[tid] = a.flag[(cta0 + p0 + tid) * HS_NW + wq];
         __syncthreads();
-        // the flag of a piece is per (run, strip, warp): uniform over this block's 32 columns.  Keep
-        // the flagged pieces only, in run order (ballot-compacted by warp 0).
+        // Unflagged records were never written; they are read anyway (in bounds) and discarded, so
+        // that all loads are independent of the flags and of each other.
         if (g == 0) {
-            for (int i0 = 0; i0 < np; i0 += 32) {
-                const int i = i0 + c;
-                long long rid = 0;
-                bool on = false;
-                if (i < np) {
-                    const int cta = p0 + i;
-                    const int seg = (int)(bs - hs_first_unit(cta, a.units, G) / a.H);
-                    rid = (long long)cta * a.nseg + seg;
-                    on = a.flag[rid * HS_NW + wq] != 0;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, on);
-                const int base = nflag_s;
-                if (on) rid_s[base + __popc(m & ((1u << c) - 1u))] = rid;
-                __syncwarp();
-                if (c == 0) nflag_s = base + __popc(m);
-                __syncwarp();
+#pragma unroll 8
+            for (int i = 0; i < np; ++i) {
+                const float v = a.rec[(cta0 + p0 + i) * a.rec_floats + D * HS_NT + xin];
+                den = __fadd_rn(den, on_s[i] ? v : 0.f);
             }
-        }
-        __syncthreads();
-        const int nf = nflag_s;
-        if (g == 0) {
-            for (int i = 0; i < nf; ++i)
-                den = __fadd_rn(den, a.rec[rid_s[i] * a.rec_floats + D * CWC + xin]);
         }
         if (k < D) {
 #pragma unroll 8
-            for (int i = 0; i < nf; ++i)
-                num = __fadd_rn(num, a.rec[rid_s[i] * a.rec_floats + k * CWC + xin]);
+            for (int i = 0; i < np; ++i) {
+                const float v = a.rec[(cta0 + p0 + i) * a.rec_floats + k * HS_NT + xin];
+                num = __fadd_rn(num, on_s[i] ? v : 0.f);
+            }
         }
     }
     den_s[g][c] = den;
@@ -430,39 +362,64 @@ static int hs_sm_count() {
     return n;
 }
 
-struct HsPlan { int S2, G, nseg; long long units, rec_floats; size_t smem; };
+struct HsPlan { int S2, GP, G; long long rec_floats; };
 
-static size_t hs_smem_bytes(int D, bool uf) {
-    return (size_t)(2 + (uf ? 1 : 0)) * D * HS_NT * sizeof(float) + (size_t)D * sizeof(float) + 16;
-}
-
-// D <= 64: a thread holds all D bins of its pixel in registers.  W % 4 == 0: the bulk copies move
-// whole 16-byte units.
+// D <= 64: a thread holds all D bins of its pixel in registers.  W % 4 == 0: TMA strides are
+// multiples of 16 bytes.
 static bool hs_plan(int B, int D, int H, int W, bool uf, HsPlan* p) {
     if (D != 16 && D != 32 && D != 64) return false;
     if (B <= 0 || H <= 0 || W <= 0 || (W & 3) != 0) return false;
-    p->smem = hs_smem_bytes(D, uf);
-    const int per_sm = (int)std::min<size_t>(8, (size_t)(227 * 1024) / (p->smem + 1024));
+    const int per_sm = uf ? HS_CTAS_PER_SM - 1 : HS_CTAS_PER_SM;
     p->S2 = (W + HS_NT - 1) / HS_NT;
-    p->units = (long long)B * p->S2 * H;
+    const long long strips = (long long)B * p->S2;
     const long long slots = (long long)hs_sm_count() * per_sm;
-    p->G = (int)(p->units < slots ? p->units : slots);
-    const long long rpc = (p->units + p->G - 1) / p->G;      // rows per CTA (max)
-    p->nseg = (int)((rpc + H - 1) / H + 1);
+    long long gp = slots / strips;              // CTAs per (item, strip): all resident at once
+    if (gp < 1) gp = 1;                         // more strips than slots: one CTA each, several waves
+    if (gp > H) gp = H;
+    if (strips * gp > 0x7fffffffLL) return false;
+    p->GP = (int)gp;
+    p->G = (int)(strips * gp);
     p->rec_floats = (long long)D * HS_NT + HS_NT;
     return true;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+typedef CUresult (*hs_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+static hs_encode_fn hs_encoder() {
+    static hs_encode_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (hs_encode_fn)f;
+    }();
+    return fn;
+}
+
+// (x, y, item*D + bin) view of a contiguous [B, D, H, W] fp32 volume, box = one row of a strip.
+static int hs_make_map(CUtensorMap* m, const float* base, int B, int D, int H, int W) {
+    hs_encode_fn enc = hs_encoder();
+    if (!enc) return DPV_E_NODEVICE;
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * D};
+    const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+    const cuuint32_t box[3] = {HS_NT, 1, (cuuint32_t)D};
+    const cuuint32_t est[3] = {1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box,
+                           est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : DPV_E_UNSUPP;
+}
+
 template <int D, int MODE, bool LOGP, bool UF>
 static int hs_launch_one(const HeadStreamArgs& a, const HsPlan& p, cudaStream_t st) {
-    static bool attr_set = false;            // per instantiation; the attribute is idempotent
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(head_stream_kernel<D, MODE, LOGP, UF>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    head_stream_kernel<D, MODE, LOGP, UF><<<dim3(p.G), dim3(HS_NT), p.smem, st>>>(a);
+    CUtensorMap mx;
+    const int rc = hs_make_map(&mx, a.x, a.B, D, a.H, a.W);
+    if (rc != 0) return rc;
+    head_stream_kernel<D, MODE, LOGP, UF><<<dim3(p.G), dim3(HS_NT), 0, st>>>(a, mx);
     DPV_LAUNCH_END();
     return 0;
 }
@@ -487,7 +444,7 @@ static int hs_launch(const HeadStreamArgs& a, const HsPlan& p, int mode, bool uf
     }
     if (rc != 0 || !uf) return rc;
     dim3 g2((a.W + 31) / 32, (D + 7) / 8, a.B), b2(32, 8);
-    uf_stream_finish_kernel<D><<<g2, b2, 0, st>>>(a, uf_out, p.G);
+    uf_stream_finish_kernel<D><<<g2, b2, 0, st>>>(a, uf_out);
     DPV_LAUNCH_END();
     return 0;
 }
@@ -498,7 +455,7 @@ static int hs_dispatch(HeadStreamArgs& a, int D, int mode, bool uf, float* uf_ou
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (!al16(a.x) || !al16(a.logp)) return DPV_E_UNSUPP;
     if (!al16(a.row_tab)) return DPV_E_BADARG;
-    a.S2 = p.S2; a.nseg = p.nseg; a.units = p.units; a.rec_floats = p.rec_floats;
+    a.S2 = p.S2; a.GP = p.GP; a.rec_floats = p.rec_floats;
     switch (D) {
         case 16: return hs_launch<16>(a, p, mode, uf, uf_out, st);
         case 32: return hs_launch<32>(a, p, mode, uf, uf_out, st);
@@ -530,7 +487,7 @@ int launch_head_stream_plain(const HeadArgs& h, cudaStream_t st) {
 extern "C" int64_t dpv_head_ufield_workspace_floats(int B, int D, int H, int W) {
     dpv::HsPlan p;
     if (!dpv::hs_plan(B, D, H, W, true, &p)) return 0;
-    const int64_t recs = (int64_t)p.G * p.nseg;
+    const int64_t recs = (int64_t)p.G;
     return recs * p.rec_floats + recs * dpv::HS_NW + 8;      // records, then per-warp flags (int32)
 }
 
@@ -606,7 +563,7 @@ extern "C" int dpv_head_ufield(const float* x, const float* d_candi, float* logp
     a.row_tab = reinterpret_cast<const int4*>(row_tab); a.col_tab = col_tab; a.intr = intr_up;
     a.depth_zero = depth_zero;
     a.B = B; a.H = H; a.W = W;
-    const int64_t recs = (int64_t)p.G * p.nseg;
+    const int64_t recs = (int64_t)p.G;
     a.rec = workspace;
     a.flag = reinterpret_cast<int*>(workspace + recs * p.rec_floats);
     a.intr_bs = intr_bstride;

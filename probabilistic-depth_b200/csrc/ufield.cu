@@ -20,7 +20,7 @@ namespace dpv {
 struct UfArgs {
     const float* dpv; const float* depth; const float* d; const float* intr; const float* mask;
     const int* row_fwd; const int* row_inv; const int* col_fwd; const int* col_inv;
-    float* uf; float* depth_zero; float* part; float* cnt;
+    float* uf; float* depth_zero; float* part; float* cnt; float* wmap;
     int B, D, H, W, mode, rows_per_chunk, nchunk;
     long long intr_bs;
     float zstart, zend, maxd1, mind, pad_depth;
@@ -29,13 +29,12 @@ struct UfArgs {
 // Weight of shifted-frame pixel (ys, xs): 1 when its back-projected point lies in the height
 // band and depth range (utils/img_utils.py:316, comparisons kept negated so NaN passes), times
 // the shifted ground-truth mask when one is given (:317-322).
+// (sy, yf) are properties of the shifted row ys alone -- its source row and (ys - cy) / fy -- and
+// are evaluated once per row of the chunk, not once per pixel.
 __device__ __forceinline__ float band_weight(const UfArgs& a, const float* __restrict__ depth_b,
-                                             const float* __restrict__ mask_b, int ys, int xs,
-                                             float fy, float cy) {
-    const int sy = a.row_fwd[ys], sx = a.col_fwd[xs];
+                                             const float* __restrict__ mask_b, int sy, float yf, int sx) {
     const bool inside = (sy >= 0) & (sx >= 0);
     const float z = inside ? __ldg(depth_b + sy * a.W + sx) : a.pad_depth;
-    const float yf = __fdiv_rn(__fsub_rn((float)ys, cy), fy);
     const float yy = __fmul_rn(yf, z);
     const bool out = (yy > a.zend) || (yy < a.zstart) || (z > a.maxd1) || (z < a.mind);
     float w = out ? 0.f : 1.f;
@@ -47,14 +46,11 @@ constexpr int UF_COLS = 32;    // columns per CTA (one warp-width: 128 B rows of
 constexpr int UF_GROUPS = 8;   // warps per CTA, each owning D/8 consecutive bins
 constexpr int UF_ROWS = 32;    // image rows per CTA (one partial sum per chunk of rows)
 
-// One CTA = 32 columns x 32 rows of one item.  Step 1: all 256 threads evaluate the per-pixel
-// weights once into shared memory (both roles of a row index: as a shifted-frame row for the
-// denominator, as an image row for the numerator).  Step 2: warp g accumulates bins
-// [g*DB, (g+1)*DB) in registers over the rows whose weight is non-zero; rows off the road band
-// cost nothing, and a row on the band is DB coalesced 128 B loads per warp.
-template <int DB>
-__global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_partial_kernel(const UfArgs a) {
-    __shared__ float w_s[UF_ROWS][UF_COLS];     // numerator weight of image pixel (r, x)
+// Kernel 1: per-pixel weights, once.  One CTA = 32 columns x 32 rows of one item.  Every thread
+// evaluates both roles of a row index (as a shifted-frame row for the denominator, as an image row
+// for the numerator), writes the numerator weight map, depth * weight, and the chunk's per-column
+// count.  Touches E[d] only (393 KB per item).
+__global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_weights_kernel(const UfArgs a) {
     __shared__ float z_s[UF_ROWS][UF_COLS];     // denominator weight of shifted pixel (r, x)
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int x = blockIdx.x * UF_COLS + lane;
@@ -66,18 +62,33 @@ __global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_partial_kernel(con
     const int r0 = chunk * UF_ROWS;
     const bool col_ok = x < a.W;
     const int xi = col_ok ? a.col_inv[x] : -1;
+    const int sx_d = col_ok ? a.col_fwd[x] : -1;              // source column of shifted column x
+    const int sx_n = (xi >= 0) ? a.col_fwd[xi] : -1;          // ... of the numerator's shifted column
+    // per row of the chunk: [0] shifted row r itself (denominator), [1] shifted row row_inv[r]
+    __shared__ int sy_s[2][UF_ROWS];
+    __shared__ float yf_s[2][UF_ROWS];
+    __shared__ int yi_s[UF_ROWS];
+    if (threadIdx.x < 2 * UF_ROWS) {
+        const int which = threadIdx.x / UF_ROWS, rr = threadIdx.x - which * UF_ROWS;
+        const int r = r0 + rr;
+        int ys = -1;
+        if (r < a.H) ys = which ? a.row_inv[r] : r;
+        if (which) yi_s[rr] = ys;
+        sy_s[which][rr] = (ys >= 0) ? a.row_fwd[ys] : -1;
+        yf_s[which][rr] = __fdiv_rn(__fsub_rn((float)ys, cy), fy);
+    }
+    __syncthreads();
     for (int rr = grp; rr < UF_ROWS; rr += UF_GROUPS) {
         const int r = r0 + rr;
         float wz = 0.f, w = 0.f;
         if (col_ok && r < a.H) {
-            wz = band_weight(a, depth_b, mask_b, r, x, fy, cy);
-            const int yi = a.row_inv[r];
-            if (yi >= 0 && xi >= 0) w = band_weight(a, depth_b, mask_b, yi, xi, fy, cy);
-            if (a.depth_zero != nullptr)
-                a.depth_zero[(long long)b * HW + r * a.W + x] = __fmul_rn(__ldg(depth_b + r * a.W + x), w);
+            wz = band_weight(a, depth_b, mask_b, sy_s[0][rr], yf_s[0][rr], sx_d);
+            if (yi_s[rr] >= 0 && xi >= 0) w = band_weight(a, depth_b, mask_b, sy_s[1][rr], yf_s[1][rr], sx_n);
+            const long long pix = (long long)b * HW + r * a.W + x;
+            a.wmap[pix] = w;
+            if (a.depth_zero != nullptr) a.depth_zero[pix] = __fmul_rn(__ldg(depth_b + r * a.W + x), w);
         }
         z_s[rr][lane] = wz;
-        w_s[rr][lane] = w;
     }
     __syncthreads();
     if (grp == 0 && col_ok) {
@@ -85,24 +96,62 @@ __global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_partial_kernel(con
         for (int rr = 0; rr < UF_ROWS; ++rr) cnt = __fadd_rn(cnt, z_s[rr][lane]);
         a.cnt[((long long)b * a.nchunk + chunk) * a.W + x] = cnt;
     }
-    const int kb = grp * DB;
+}
+
+// Kernel 2: masked column sums.  One CTA = a 32 x 32 pixel tile x 16 bins; warp g owns bins
+// [kb, kb + DB) and accumulates them in registers over the rows whose weight is non-zero.  Tiles
+// off the road band do no volume traffic at all.
+template <int DB, int NB>
+__global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_partial_kernel(const UfArgs a) {
+    __shared__ float w_s[UF_ROWS][UF_COLS];     // numerator weight of image pixel (r, x)
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int x = blockIdx.x * UF_COLS + lane;
+    // blockIdx.z = item * nbg + bin group: the CTA owns UF_GROUPS * DB consecutive bins
+    const int nbg = (a.D + UF_GROUPS * DB - 1) / (UF_GROUPS * DB);
+    const int chunk = blockIdx.y, b = blockIdx.z / nbg, bg = blockIdx.z - b * nbg;
+    const int HW = a.H * a.W;
+    const int r0 = chunk * UF_ROWS;
+    const bool col_ok = x < a.W;
+    // tile-level skip only: a tile with any pixel on the band streams all of its rows (off-band rows
+    // are multiplied by a zero weight), which keeps the inner loop free of bookkeeping.
+    float wcol[UF_ROWS / UF_GROUPS];
+    bool mine = false;
+#pragma unroll
+    for (int i = 0; i < UF_ROWS / UF_GROUPS; ++i) {
+        const int rr = grp + i * UF_GROUPS, r = r0 + rr;
+        wcol[i] = (col_ok && r < a.H) ? __ldg(a.wmap + (long long)b * HW + r * a.W + x) : 0.f;
+        w_s[rr][lane] = wcol[i];
+        mine |= wcol[i] != 0.f;
+    }
+    const int any = __syncthreads_or(mine ? 1 : 0);
+    const int kb = (bg * UF_GROUPS + grp) * DB;
     if (kb >= a.D) return;
     float acc[DB];
 #pragma unroll
     for (int j = 0; j < DB; ++j) acc[j] = 0.f;
-    const float* dpv_b = a.dpv + ((long long)b * a.D + kb) * HW + x;
-    for (int rr = 0; rr < UF_ROWS; ++rr) {
-        const float w = w_s[rr][lane];
-        if (!__any_sync(0xffffffffu, w != 0.f)) continue;
-        if (w != 0.f) {
-            const float* col = dpv_b + (long long)(r0 + rr) * a.W;
-            float v[DB];
+    if (any) {
+        const float* dpv_b = a.dpv + ((long long)b * a.D + kb) * HW + (long long)r0 * a.W + (col_ok ? x : 0);
+        const int rows = min(UF_ROWS, a.H - r0);
 #pragma unroll
-            for (int j = 0; j < DB; ++j) v[j] = (kb + j < a.D) ? ld_stream(col + (long long)j * HW) : 0.f;
+        for (int g0 = 0; g0 < UF_ROWS; g0 += NB) {
+            float v[NB][DB];
 #pragma unroll
-            for (int j = 0; j < DB; ++j) {
-                const float pr = (a.mode == DPV_IN_PROB) ? v[j] : expf(v[j]);
-                acc[j] = __fadd_rn(acc[j], __fmul_rn(pr, w));
+            for (int i = 0; i < NB; ++i) {
+                const float* col = dpv_b + (g0 + i) * a.W;
+#pragma unroll
+                for (int j = 0; j < DB; ++j)
+                    v[i][j] = (g0 + i < rows && kb + j < a.D) ? ld_stream(col + (long long)j * HW)
+                                                              : ((a.mode == DPV_IN_PROB) ? 0.f : -INFINITY);
+            }
+            // rows are added in increasing order; a zero weight contributes +0
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const float w = w_s[g0 + i][lane];
+#pragma unroll
+                for (int j = 0; j < DB; ++j) {
+                    const float pr = (a.mode == DPV_IN_PROB) ? v[i][j] : __expf(v[i][j]);
+                    acc[j] = __fadd_rn(acc[j], __fmul_rn(pr, w));
+                }
             }
         }
     }
@@ -132,7 +181,8 @@ static int ufield_row_chunks(int H) { return (H + dpv::UF_ROWS - 1) / dpv::UF_RO
 
 extern "C" int64_t dpv_ufield_workspace_floats(int B, int D, int H, int W) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
-    return (int64_t)B * ufield_row_chunks(H) * (D + 1) * W;
+    // partial sums [B,chunks,D,W] + counts [B,chunks,W] + weight map [B,H,W]
+    return (int64_t)B * ufield_row_chunks(H) * (D + 1) * W + (int64_t)B * H * W;
 }
 
 extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_candi,
@@ -147,7 +197,6 @@ extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_c
     DPV_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0);
     DPV_CHECK_ARG(in_mode == DPV_IN_LOGPROB || in_mode == DPV_IN_PROB);
     if (B > 65535 || D > 65535) return DPV_E_UNSUPP;
-    if (D > 32 * UF_GROUPS) return DPV_E_UNSUPP;
     UfArgs a;
     a.dpv = dpv; a.depth = depth; a.d = d_candi; a.intr = intr_up; a.mask = mask;
     a.row_fwd = row_fwd; a.row_inv = row_inv; a.col_fwd = col_fwd; a.col_inv = col_inv;
@@ -157,16 +206,21 @@ extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_c
     a.rows_per_chunk = UF_ROWS;
     a.part = workspace;
     a.cnt = workspace + (long long)B * a.nchunk * D * W;
+    a.wmap = a.cnt + (long long)B * a.nchunk * W;
     a.intr_bs = intr_bstride;
     a.zstart = zstart; a.zend = zend; a.maxd1 = maxd - 1.0f; a.mind = mind;
     a.pad_depth = pad_depth;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((W + UF_COLS - 1) / UF_COLS, a.nchunk, B), block(UF_COLS * UF_GROUPS);
-    const int db = (D + UF_GROUPS - 1) / UF_GROUPS;
-    if (db <= 4) ufield_partial_kernel<4><<<grid, block, 0, st>>>(a);
-    else if (db <= 8) ufield_partial_kernel<8><<<grid, block, 0, st>>>(a);
-    else if (db <= 16) ufield_partial_kernel<16><<<grid, block, 0, st>>>(a);
-    else ufield_partial_kernel<32><<<grid, block, 0, st>>>(a);
+    // Every warp owns 4 bins of a 32 x 32 pixel tile and has 16 rows x 4 bins of loads in flight;
+    // only the tiles on the road band do any volume traffic (about a third on KITTI-like frames).
+    constexpr int DB = 4, NB = 16;
+    const int nbg = (D + UF_GROUPS * DB - 1) / (UF_GROUPS * DB);
+    if ((long long)B * nbg > 65535) return DPV_E_UNSUPP;
+    dim3 grid0((W + UF_COLS - 1) / UF_COLS, a.nchunk, B), block(UF_COLS * UF_GROUPS);
+    ufield_weights_kernel<<<grid0, block, 0, st>>>(a);
+    DPV_LAUNCH_END();
+    dim3 grid((W + UF_COLS - 1) / UF_COLS, a.nchunk, B * nbg);
+    ufield_partial_kernel<DB, NB><<<grid, block, 0, st>>>(a);
     DPV_LAUNCH_END();
     dim3 grid2((W + 127) / 128, D, B), block2(128);
     ufield_finish_kernel<<<grid2, block2, 0, st>>>(a);

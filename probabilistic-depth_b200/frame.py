@@ -19,7 +19,7 @@ from . import _lib, ops
 
 class FrameStep:
     def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None,
-                 fuse_uf=True):
+                 fuse_uf=False):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dev = dev
         self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W = B, V, C, D, h, w, H, W
@@ -38,7 +38,10 @@ class FrameStep:
         self.uf = e(B, D, W)
         self.dz = e(B, H, W)
         self.lib = _lib.load()
-        # K3 + K5 in one pass when the shape allows it, else dpv_head followed by dpv_ufield
+        # K3 + K5 either as dpv_head followed by dpv_ufield (default: the short-CTA head kernel runs at
+        # ~85 % of the HBM roof and the UF pass re-reads only the road-band tiles) or in one pass with
+        # the persistent TMA-fed kernel (fuse_uf=True; same step time at 8 x 256 x 384, see
+        # profiles/README.md)
         self.tabs = ops.uf_fused_tables(H, W, ops.KITTI_UF["pshift"], dev) if fuse_uf else None
         nfused = int(self.lib.dpv_head_ufield_workspace_floats(B, D, H, W)) if self.tabs else 0
         self.fused_uf = nfused > 0
@@ -131,6 +134,6 @@ class FrameStep:
         B, D, HW = self.B, self.D, self.H * self.W
         head = 8 * HW * D + 16 * HW
         if self.fused_uf:
-            return "dpv::head_vec_kernel<4,LOGITS,...,UF> (full-res head + UF, fused)", \
+            return "dpv::head_stream_kernel<64,LOGITS,LOGP,UF> (full-res head + UF, fused, TMA-fed)", \
                 B * (head + 4 * D * self.W + 4 * HW)
-        return "dpv::head_vec_kernel<4,LOGITS> (full-res head)", B * head
+        return "dpv::head_kernel<64,1,LOGITS,...> (full-res head)", B * head

@@ -274,8 +274,12 @@ def test_head_ufield_fused_vs_golden(dpv, golden, name):
     out = dpv.ops.head_ufield(x, c["d_candi"], cu(c["intr_up"]), mode="logits", logp=True, depth=True,
                               variance=True, argmax=True, quarter=True)
     plain = dpv.ops.head(x, c["d_candi"], logp=True, depth=True, variance=True, argmax=True, quarter=True)
-    for k in ("logp", "depth", "variance", "argmax", "quarter"):
-        assert torch.equal(out[k], plain[k]), k
+    # dpv_head may take a different kernel (bins split over lanes for small volumes): same values up
+    # to the order of the per-pixel sums
+    assert torch.equal(out["argmax"], plain["argmax"])
+    assert torch.equal(out["quarter"], out["logp"][:, :, ::4, ::4])
+    for k in ("logp", "depth", "variance"):
+        assert float(((out[k] - plain[k]).abs() / plain[k].abs().clamp_min(1.0)).max()) < 1e-5, k
     want_uf, want_dz = g[name + "_uf"], g[name + "_depthzero"]
     keep = ~_near_threshold_columns(c, True)
     assert keep.mean() > 0.9
@@ -285,7 +289,7 @@ def test_head_ufield_fused_vs_golden(dpv, golden, name):
     np.testing.assert_allclose(out["depth_zero"].cpu().numpy()[:, :, keep], want_dz[:, :, keep], rtol=1e-4, atol=0)
     # the two-kernel path (dpv_head + dpv_ufield) takes the same per-pixel decisions: same NaN
     # pattern and depth_zero everywhere, UF equal up to the summation order
-    uf2, dz2 = dpv.ops.ufield(plain["logp"], c["d_candi"], cu(c["intr_up"]), depth=plain["depth"])
+    uf2, dz2 = dpv.ops.ufield(out["logp"], c["d_candi"], cu(c["intr_up"]), depth=out["depth"])
     assert torch.equal(out["depth_zero"], dz2)
     assert torch.equal(torch.isnan(out["uf"]), torch.isnan(uf2))
     ok = ~torch.isnan(uf2)
@@ -373,13 +377,14 @@ def test_host_pipeline_matches_ops(dpv):
     hd = dpv.ops.head(cu(logits), d, logp=True, depth=True, variance=True, argmax=True, quarter=True)
     uf, dz = dpv.ops.ufield(hd["logp"], d, cu(cam["intrinsics_up"]), depth=hd["depth"])
     assert torch.equal(out["bv"], bv.cpu())
-    assert torch.equal(out["depth"], hd["depth"].cpu())
-    assert torch.equal(out["variance"], hd["variance"].cpu())
+    # the pipeline runs head + UF fused (another kernel than dpv_head): same values up to the order
+    # of the per-pixel sums, same arg-max
+    for k in ("depth", "variance", "quarter"):
+        np.testing.assert_allclose(out[k].numpy(), hd[k].cpu().numpy(), rtol=1e-5, atol=1e-6)
     assert torch.equal(out["argmax"], hd["argmax"].cpu())
-    assert torch.equal(out["quarter"], hd["quarter"].cpu())
     # the pipeline runs head + UF fused, item by item: same per-pixel decisions, and a UF equal up
     # to the order in which the rows of a column are added
     assert torch.equal(torch.isnan(out["uf"]), torch.isnan(uf.cpu()))
     np.testing.assert_allclose(out["uf"].numpy(), uf.cpu().numpy(), rtol=1e-5, atol=1e-30, equal_nan=True)
-    assert torch.equal(out["depth_zero"], dz.cpu())
+    np.testing.assert_allclose(out["depth_zero"].numpy(), dz.cpu().numpy(), rtol=1e-5, atol=0)
     pipe.close()

@@ -16,7 +16,12 @@ ops = dpv.ops
 PEAK = 6554.9
 
 
+GRAPH = False
+
+
 def timeit(fn, nrot, iters=20, warm=3):
+    if GRAPH:
+        return timeit_graph(fn, nrot, iters, warm)
     for i in range(warm):
         fn(i % nrot)
     torch.cuda.synchronize()
@@ -30,12 +35,44 @@ def timeit(fn, nrot, iters=20, warm=3):
     return ts[len(ts) // 2], ts[0]
 
 
+def timeit_graph(fn, nrot, iters=20, warm=3):
+    """One CUDA graph holding `nrot` back-to-back calls (rotating inputs): device time per call with
+    no host launch overhead in the way."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(max(warm, nrot)):
+            fn(i % nrot)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    keep = []
+    with torch.cuda.graph(g):
+        for i in range(nrot):
+            keep.append(fn(i))
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / nrot)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--graph", action="store_true")
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--only", default="")
     ap.add_argument("--pose", default="stereo")
     args = ap.parse_args()
+    global GRAPH
+    GRAPH = args.graph
     B, V, C, D, h, w, H, W = args.B, 1, 67, 64, 64, 96, 256, 384
     s = dpv.synth
     d = s.depth_candidates(5, 40, D)
