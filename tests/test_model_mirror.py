@@ -1,0 +1,113 @@
+"""models/models.py:BaseModel mirror against the reference BaseModel.
+
+CPU part: same state_dict keys, shapes and (under the same torch seed) the same random-init
+weights as the reference -- checked against the list make_model_golden.py stored, and against the
+reference itself when /root/reference is present.  The reference loads checkpoints by POSITION
+(trainer/base_trainer.py:83-90), so order and shapes are the contract.
+GPU part: forward of all three nmodes on the sm_100a kernels vs the reference's CPU outputs
+(tests/golden/model.npz); cuDNN convolutions run in full fp32 (TF32 off).
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import model_cases as MC  # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "model.npz"))
+
+
+def _ours(name):
+    OM = importlib.import_module("probabilistic-depth_b200.models.models")
+    torch.manual_seed(0)
+    return OM.BaseModel(MC.cfg(name), 0)
+
+
+@pytest.mark.parametrize("name", sorted(MC.MODES))
+def test_state_dict_matches_reference_order_shapes_and_init(name):
+    sd = _ours(name).state_dict()
+    assert list(sd.keys()) == list(GOLD[name + "_keys"])
+    assert [str(tuple(v.shape)) for v in sd.values()] == list(GOLD[name + "_shapes"])
+    sums = np.array([float(v.double().sum()) for v in sd.values()])
+    np.testing.assert_allclose(sums, GOLD[name + "_sums"], rtol=1e-12, atol=1e-12)
+    assert len(sd) == {"default": 385, "default_upsample": 205, "default_feedback": 404}[MC.MODES[name][0]]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_weights_bit_identical_to_reference_under_same_seed():
+    import warnings
+    warnings.filterwarnings("ignore")
+    import make_golden
+    make_golden.import_reference()
+    import models.models as RM
+    for name in sorted(MC.MODES):
+        torch.manual_seed(0)
+        ref = RM.BaseModel(MC.cfg(name), 0).state_dict()
+        ours = _ours(name).state_dict()
+        assert all(torch.equal(ref[k], ours[k]) for k in ref), name
+
+
+def _run(model, name, device):
+    outs, prev = [], None
+    for f in range(MC.MODES[name][3]):
+        mi = MC.frame_inputs(name, f)
+        t = {k: (torch.from_numpy(v).to(device) if isinstance(v, np.ndarray) and k != "d_candi" else v)
+             for k, v in mi.items()}
+        t["prev_output"] = prev
+        with torch.no_grad():
+            res = model([t])[0]
+        outs.append(res)
+        prev = torch.nn.functional.interpolate(res["output_refined"][-1], scale_factor=0.25, mode="nearest")
+    return outs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MC.MODES))
+def test_forward_matches_reference_outputs(name):
+    dpv = importlib.import_module("probabilistic-depth_b200")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = _ours(name).cuda().eval()
+    nmode = MC.MODES[name][0]
+    launches0 = dpv._lib.launch_count()
+    outs = _run(model, name, "cuda")
+    assert dpv._lib.launch_count() - launches0 >= 3 * len(outs)       # the hot path ran on our kernels
+    for f, res in enumerate(outs):
+        assert set(res) == {"output", "output_refined", "flow", "flow_refined"}
+        assert len(res["output"]) == (1 if nmode == "default" else 2)
+        bv = res["output"][0] if nmode == "default_upsample" else res["output"][-1]
+        refined = res["output_refined"][-1]
+        assert tuple(bv.shape) == (1, MC.D, MC.H // 4, MC.W // 4) and tuple(refined.shape) == (1, MC.D, MC.H, MC.W)
+        # ~60 fp32 conv layers on cuDNN vs the CPU: 1e-3-class agreement on log-probabilities
+        want_bv, want_rf = GOLD["%s_f%d_bv" % (name, f)], GOLD["%s_f%d_refined" % (name, f)]
+        got_bv, got_rf = bv[:, :, ::2, ::2].cpu().numpy(), refined[:, :, ::8, ::8].cpu().numpy()
+        assert np.max(np.abs(got_bv - want_bv) / np.maximum(1.0, np.abs(want_bv))) < 2e-3
+        assert np.max(np.abs(got_rf - want_rf) / np.maximum(1.0, np.abs(want_rf))) < 2e-3
+        iu = dpv.utils.img_utils
+        dq = iu.dpv_to_depthmap(bv, MC.D_CANDI, BV_log=True).cpu().numpy()
+        dr = iu.dpv_to_depthmap(refined, MC.D_CANDI, BV_log=True).cpu().numpy()
+        np.testing.assert_allclose(dq, GOLD["%s_f%d_depth_q" % (name, f)], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(dr, GOLD["%s_f%d_depth" % (name, f)], rtol=2e-3, atol=2e-3)
+        # log-DPVs are normalised
+        assert float((torch.logsumexp(refined, 1)).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_batched_forward_equals_per_item_forward():
+    """One launch per batch (ours) == the reference's per-item loop semantics: a batch of 2
+    different items gives the items' individual results (bn_avg=True: BN uses running stats)."""
+    name = "default_stereo"
+    torch.backends.cudnn.allow_tf32 = False
+    model = _ours(name).cuda().eval()
+    a, b = MC.frame_inputs(name, 0), MC.frame_inputs(name, 1)
+    cat = {k: (np.concatenate([a[k], b[k]]) if k != "d_candi" else a[k]) for k in a}
+    to = lambda d: {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) and k != "d_candi" else v) for k, v in d.items()}
+    with torch.no_grad():
+        both = model([to(cat)])[0]["output_refined"][0]
+        one = model([to(b)])[0]["output_refined"][0]
+    assert float((both[1:] - one).abs().max()) < 2e-3

@@ -96,3 +96,29 @@ def test_correlation(golden, name):
     c = cases.corr_case(name)
     y = O.local_correlation(T(c["x1"]), T(c["x2"]), 4)
     np.testing.assert_array_equal(y.numpy(), golden("correlation")[name])
+
+
+# ------------------------------------------------- second restatement: ATen ops tap by tap
+from oracle import dpv_oracle_np as ONP   # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["mono_small", "mono_yaw_2view", "stereo_small", "oob_heavy", "odd_dims"])
+@pytest.mark.parametrize("dist", ["L2", "L1"])
+def test_numpy_restatement_sweep(golden, name, dist):
+    """grid_sample(bilinear, zeros, align_corners=False) restated in numpy reproduces the
+    reference's est_swp_volume_v4 outputs (so the torch-based oracle is not self-referential)."""
+    c = cases.sweep_case(name)
+    want = golden("sweep")[name + "_" + dist]
+    got = ONP.plane_sweep_cost(c["ref"], c["src"], c["d_candi"], c["R"], c["t"], c["K"], c["rays"],
+                               c["sigma"], dist)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+
+
+def test_numpy_restatement_warp_feature_and_softmax(golden):
+    name = cases.WARP_FEATURE_CASES[0]
+    c = cases.warp_feature_case(name)
+    got = ONP.warp_feature_diag(c["feat"], c["d_candi"], c["R"], c["t"], c["K"], c["rays"])
+    np.testing.assert_allclose(got, golden("warp_feature")[name], rtol=2e-5, atol=2e-5)
+    s = cases.softmax_case("small")
+    np.testing.assert_allclose(ONP.log_softmax(s["x"], 1), golden("softmax")["small_logdpv"],
+                               rtol=1e-5, atol=2e-6)

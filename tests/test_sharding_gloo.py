@@ -1,0 +1,132 @@
+"""Multi-process (gloo, world_size 2, CPU) checks of the N > 1 host logic in sharding.py:
+
+* unit round-robin (items / sequences) covers every unit exactly once and merges back in order;
+* the depth-plane-sharded soft-max exchange protocol (PlaneShardedHead) reproduces the single-rank
+  log-softmax / E[d] / Var / arg-max when the local passes are done by a stand-in that restates the
+  dpv_shard_* kernels with torch CPU ops.  The stand-in is TEST code: the product's local passes
+  are the CUDA kernels (sharding.CudaShardKernels) and there is no CPU implementation in the
+  package; on the GPU box the same protocol runs over NCCL (tests/test_gpu_parity.py).
+"""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+class TorchShardStandIn:
+    """What csrc/shard.cu computes, in torch CPU ops (test stand-in for CudaShardKernels)."""
+
+    def local_max(self, x, lo, want_argmax):
+        m, am = x.max(dim=1)
+        # first maximum wins inside the shard, as shard_max_kernel's strict '>' does
+        first = (x == m.unsqueeze(1)).float().argmax(dim=1)
+        return m.contiguous(), (first + lo).float().contiguous() if want_argmax else None
+
+    def local_sums(self, x, d_local, gmax):
+        e = torch.exp(x - gmax.unsqueeze(1))
+        return torch.stack([e.sum(1), (e * d_local.view(1, -1, 1)).sum(1)]).contiguous()
+
+    def local_central(self, x, d_local, gmax, gsums):
+        e = torch.exp(x - gmax.unsqueeze(1))
+        mean = gsums[1] / gsums[0]
+        dd = d_local.view(1, -1, 1) - mean.unsqueeze(1)
+        return (dd * dd * e).sum(1).contiguous()
+
+    def finish(self, x, gmax, gsums, gcentral, want_logp, want_depth):
+        ls = torch.log(gsums[0])
+        logp = (x - gmax.unsqueeze(1)) - ls.unsqueeze(1) if want_logp else None
+        depth = gsums[1] / gsums[0] if want_depth else None
+        var = gcentral / gsums[0] if gcentral is not None else None
+        return logp, depth, var
+
+    def argmax_merge(self, vals, idx):
+        best, bi = vals[0].reshape(-1).clone(), idx[0].reshape(-1).clone()
+        for g in range(1, vals.shape[0]):
+            v, i = vals[g].reshape(-1), idx[g].reshape(-1)
+            take = v > best
+            best = torch.where(take, v, best)
+            bi = torch.where(take, i, bi)
+        return bi.long()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sharding = importlib.import_module("probabilistic-depth_b200.sharding")
+        synth = importlib.import_module("probabilistic-depth_b200.synth")
+        # ---- units: every rank takes r, r+G, ...; gather and merge -----------------------------
+        n_units = 7
+        mine = sharding.shard_units(n_units, rank, world)
+        results = [u * 10 + 1 for u in mine]                      # "process" the unit
+        gathered = [None] * world
+        dist.all_gather_object(gathered, results)
+        merged = sharding.merge_units(gathered, n_units)
+        assert merged == [u * 10 + 1 for u in range(n_units)]
+        t = torch.arange(n_units * 3).reshape(n_units, 3)
+        assert torch.equal(sharding.shard_slice(t, rank, world), t[rank::world])
+        assert sharding.max_over_ranks(float(rank + 1)) == float(world)
+
+        # ---- planes: sharded soft-max == single-rank soft-max ----------------------------------
+        B, D, H, W = 2, 10, 5, 7                                   # D not divisible by 4 ranks either
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn((B, D, H, W), generator=g) * 4.0
+        x[0, 3, 0, :] = x[0, 8, 0, :] = 50.0                       # tie across the two shards: first wins
+        d = synth.depth_candidates(5.0, 40.0, D, 1.0)
+        lo, hi = sharding.plane_range(D, rank, world)
+        head = sharding.PlaneShardedHead(D, local=TorchShardStandIn())
+        assert (head.lo, head.hi) == (lo, hi)
+        out = head(x[:, lo:hi].contiguous(), d)
+        ref = torch.log_softmax(x, 1)
+        dd = torch.from_numpy(d.astype(np.float32)).view(1, D, 1, 1)
+        p = ref.exp()
+        mean = (p * dd).sum(1)
+        var = (p * (dd - mean.unsqueeze(1)) ** 2).sum(1)
+        assert float((out["logp"] - ref[:, lo:hi]).abs().max()) < 1e-5
+        assert float((out["depth"] - mean).abs().max()) < 1e-4
+        assert float(((out["variance"] - var).abs() / var.clamp_min(1e-3)).max()) < 1e-4
+        assert torch.equal(out["argmax"], torch.argmax(ref, 1))
+        # every rank ends up with the same replicated per-pixel products
+        rep = [None] * world
+        dist.all_gather_object(rep, (out["depth"].numpy().tobytes(), out["argmax"].numpy().tobytes()))
+        assert all(r == rep[0] for r in rep)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_unit_and_plane_sharding_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def test_plane_range_partitions_every_plane_once():
+    sharding = importlib.import_module("probabilistic-depth_b200.sharding")
+    for D in (64, 128, 10, 7):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.plane_range(D, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == D
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
