@@ -201,7 +201,8 @@ class Base3D(nn.Module):
         for i, blk in enumerate(self.dres_modules):
             if next(blk.parameters()).device != x.device:
                 self.dres_modules[i] = blk = blk.to(x.device)
-            blk.train(self.training)
+            # unregistered, hence never reached by .eval(): they stay in training mode (batch
+            # statistics), in the reference and here
             x = blk(x) + x
         return self.classify(x).squeeze(1)
 

@@ -5,7 +5,7 @@ Run in the build container only (needs /root/reference):  python tests/golden/ma
 Random-init weights under torch.manual_seed(0) (our BaseModel creates and initialises its
 modules in the same order, so the same seed gives the same weights: tests/test_model_mirror.py
 checks that against the key / shape / checksum list stored here), seeded synthetic inputs from
-model_cases.py, model.eval().  Stored per mode and frame: the 1/4-res log-DPV at every 2nd pixel,
+model_cases.py, BatchNorm in batch-statistics mode (model_cases.batch_stat_norm explains why).  Stored per mode and frame: the 1/4-res log-DPV at every 2nd pixel,
 the refined log-DPV at every 8th pixel, and E[d] of both.
 """
 import os
@@ -30,7 +30,7 @@ def main():
     out = {}
     for name, (nmode, bn_avg, kind, frames) in MC.MODES.items():
         torch.manual_seed(0)
-        model = RM.BaseModel(MC.cfg(name), 0).eval()
+        model = MC.batch_stat_norm(RM.BaseModel(MC.cfg(name), 0))
         sd = model.state_dict()
         out[name + "_keys"] = np.array(list(sd.keys()))
         out[name + "_shapes"] = np.array([str(tuple(v.shape)) for v in sd.values()])
@@ -51,7 +51,12 @@ def main():
             out["%s_f%d_depth" % (name, f)] = IU.dpv_to_depthmap(refined, MC.D_CANDI, BV_log=True).numpy()
             # feedback hand-off exactly as trainer/default_trainer.py:221-222
             prev = torch.nn.functional.interpolate(refined, scale_factor=0.25, mode="nearest")
-            print(name, f, "bv", tuple(bv.shape), "refined", tuple(refined.shape))
+            if f + 1 < frames:
+                # the next frame's prev_output: stored so that the mirror can be fed the reference's
+                # own hand-off (frame-to-frame error does not compound in the comparison)
+                out["%s_f%d_prev" % (name, f + 1)] = prev.numpy()
+            print(name, f, "bv", tuple(bv.shape), float(bv.min()), "refined", tuple(refined.shape), float(refined.min()),
+                  "depth range", float(out["%s_f%d_depth" % (name, f)].min()), float(out["%s_f%d_depth" % (name, f)].max()))
     np.savez_compressed(os.path.join(HERE, "model.npz"), **out)
     print("wrote model.npz", os.path.getsize(os.path.join(HERE, "model.npz")) / 1e6, "MB")
 

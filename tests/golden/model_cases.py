@@ -40,3 +40,23 @@ def frame_inputs(name, frame, batch=1):
     dm, mk = synth.sparse_depth(seed + 1, batch, H // 4, W // 4)
     return dict(rgb=synth.randn(seed, batch, 2, 3, H, W), intrinsics=cam["intrinsics"],
                 unit_ray=cam["unit_ray"], src_cam_poses=poses, d_candi=D_CANDI, dmaps=dm, masks=mk)
+
+
+def batch_stat_norm(model):
+    """Put the BatchNorm layers (only) in batch-statistics mode.
+
+    With random-init weights and identity running statistics the activations of the ~60-layer
+    network grow to ~1e12 and the soft-max input is quantised at 65536 per ulp: nothing can be
+    compared there.  Normalising with the batch statistics (deterministic for a given input) keeps
+    every stage O(1-100); the reference and the mirror are driven the same way.  This is also what
+    the reference itself does in eval with bn_avg=false (models/models.py:25-30)."""
+    import torch.nn as nn
+    model.eval()
+    for m in model.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.train()
+    for blk in getattr(getattr(model, "based_3d", None), "dres_modules", []):
+        for m in blk.modules():
+            if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                m.train()
+    return model
