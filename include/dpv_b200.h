@@ -66,7 +66,9 @@ long long dpv_launch_count(void);
  * log_softmax_out : optional [B, D, H, W]; when non-null additionally receives
  *         log_softmax(cost, dim=1) (models/packnet.py:394 places them back to back).
  * algo  : 0 = choose, 1 = direct per-plane gather (L1 or L2), 2 = per-cell Gram form with global
- *         gathers (L2), 3 = per-cell Gram form staged through shared memory (L2, production path).
+ *         gathers (L2), 3 = per-cell Gram form staged through shared memory with cp.async (L2),
+ *         4 = per-cell Gram form, TMA-fed, four lanes per pixel (L2, production path; needs W % 4 == 0
+ *         and 16-byte aligned ref/src bases and strides -- "choose" falls back to 3/2 otherwise).
  */
 int dpv_sweep_cost_volume(const float* ref, const float* src, const float* pose, const float* K,
                           const float* rays, const float* d_candi, float* cost,

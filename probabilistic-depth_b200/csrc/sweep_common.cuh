@@ -38,5 +38,8 @@ __device__ __forceinline__ CellTaps cell_taps(const Tap& t, int H, int W) {
 
 // Defined in sweep_tiled.cu: shared-memory staged variant of the Gram formulation.
 int launch_sweep_gram_tiled(const SweepArgs& a, cudaStream_t st);
+// Defined in sweep_tma.cu: TMA-fed variant, four lanes per reference pixel (production path).
+bool sweep_gram_tma_supported(const SweepArgs& a);
+int launch_sweep_gram_tma(const SweepArgs& a, cudaStream_t st);
 
 }  // namespace dpv

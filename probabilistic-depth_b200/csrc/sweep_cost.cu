@@ -226,11 +226,10 @@ extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const f
     DPV_CHECK_ARG(ref && src && pose && K && rays && d_candi && cost);
     DPV_CHECK_ARG(B > 0 && V > 0 && C > 0 && D > 0 && H > 0 && W > 0);
     DPV_CHECK_ARG(dist == DPV_DIST_L2 || dist == DPV_DIST_L1);
-    DPV_CHECK_ARG(algo >= 0 && algo <= 3);
+    DPV_CHECK_ARG(algo >= 0 && algo <= 4);
     if ((long long)H * W > (1LL << 30) || B > 65535) return DPV_E_UNSUPP;
     if (algo >= 2 && dist != DPV_DIST_L2) return DPV_E_UNSUPP;
     if (algo == 3 && log_softmax_out != nullptr) return DPV_E_UNSUPP;
-    if (algo == 0) algo = (dist != DPV_DIST_L2) ? 1 : (log_softmax_out != nullptr ? 2 : 3);
     constexpr int NT = 32;
     SweepArgs a;
     a.ref = ref; a.src = src; a.pose = pose; a.K = K; a.rays = rays; a.d = d_candi;
@@ -241,6 +240,12 @@ extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const f
     a.sigma = sigma;
     const int HW = H * W;
     a.PS = pick_plane_split(B, HW, D, log_softmax_out != nullptr);
+    if (algo == 0) {
+        if (dist != DPV_DIST_L2) algo = 1;
+        else if (sweep_gram_tma_supported(a)) algo = 4;
+        else algo = (log_softmax_out != nullptr) ? 2 : 3;
+    }
+    if (algo == 4) return launch_sweep_gram_tma(a, (cudaStream_t)stream);
     if (algo == 3) return launch_sweep_gram_tiled(a, (cudaStream_t)stream);
     const int kper = (D + a.PS - 1) / a.PS;
     const size_t smem = (size_t)kper * (NT + 1) * sizeof(float);

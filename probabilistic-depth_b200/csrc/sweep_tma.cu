@@ -1,0 +1,537 @@
+// K1 + K2a, TMA-fed Gram kernel with four threads per reference pixel (production path for the L2
+// cost volume; algo = 4).
+//
+// Same mathematics as sweep_gram_tiled_kernel (sweep_tiled.cu): per reference pixel the D sampling
+// positions fall into a handful of source 2x2 cells ("runs" of consecutive planes); for each run
+// the channel contraction is the 4x4 Gram matrix of (tap - ref) differences, and every plane of the
+// run is a 10-term quadratic form in its bilinear weights.  What changed is the mapping onto the
+// machine (ncu on the tiled kernel, profiles/r01_*: one thread per pixel gives 10 warps per SM at
+// the model's 8 x 64 x 96 pixels, and a quarter of its instructions were 4-byte cp.async copies):
+//   * a CTA owns one row segment of 32 reference pixels, FOUR adjacent lanes per pixel.  The
+//     lanes split the planes for run detection (each walks D/4 planes, the run lists are stitched
+//     with two warp shuffles), split the runs round-robin for the Gram accumulation (NSLOT
+//     Gram matrices of 10 registers per lane instead of 6 x 10 per thread) and evaluate the planes
+//     of their own runs.  4x the threads at ~half the registers: 24 warps per SM instead of 10.
+//   * the source window of the tile and the reference pixels are fetched by the TMA engine
+//     (cp.async.bulk.tensor, 5-D / 4-D maps over the caller's strided [B,V,C,H,W] / [B,C,H,W]
+//     tensors): one elected thread issues one box per window row and chunk of 8 channels,
+//     completion is counted in bytes on an mbarrier, and out-of-image taps / channels past C are
+//     zero-filled by the engine -- grid_sample's zeros padding costs no instruction.
+//   * results are collected in shared memory ([plane][pixel]) and written with 128-byte rows.
+// Shared memory: stage layout [row][channel][col] so that the four taps of a cell and the channels
+// of a chunk are compile-time offsets from one per-run base (LDS with immediate offsets).
+// Tiles whose window does not fit (very large motion) gather from global memory instead.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "sweep_common.cuh"
+
+namespace dpv {
+
+constexpr int TM_PX = 32, TM_T = 4, TM_NT = TM_PX * TM_T;
+constexpr int TM_WC = 52, TM_WR = 8;             // source window capacity (cols, rows)
+constexpr int TM_CK = 8;                         // channels per stage
+constexpr int TM_NSTAGE = 2;
+constexpr int TM_MAXRUN = 32;                    // runs recorded per pixel and view
+constexpr int TM_ROW = TM_CK * TM_WC;            // floats of one window row (all channels of a chunk)
+constexpr int TM_WIN = TM_WR * TM_ROW;
+constexpr int TM_STAGE = TM_WIN + TM_CK * TM_PX; // + the reference pixels of the chunk
+constexpr int TM_OS = TM_PX + 1;                 // row stride of the result tile (bank spread)
+constexpr int kTmOutside = -1;                   // cell id of "no tap inside the image"
+constexpr int kTmNone = -2;
+
+__device__ __forceinline__ unsigned tm_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tm_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tm_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tm_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tm_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tm_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(tm_smem(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tm_load_5d(void* dst, const CUtensorMap* map, int x, int y, int c, int v,
+                                           int b, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(tm_smem(dst)), "l"(map), "r"(x), "r"(y), "r"(c), "r"(v), "r"(b), "r"(tm_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_load_4d(void* dst, const CUtensorMap* map, int x, int y, int c, int b,
+                                           unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(tm_smem(dst)), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(tm_smem(bar))
+                 : "memory");
+}
+
+// in-image cells have x0 in [-1, W-1], y0 in [-1, H-1]: packed ids are non-negative (W, H < 32767)
+__device__ __forceinline__ int tm_pack(int x0, int y0) { return ((y0 + 1) << 16) | (x0 + 1); }
+__device__ __forceinline__ int tm_cell_x(int p) { return (p & 0xffff) - 1; }
+__device__ __forceinline__ int tm_cell_y(int p) { return (p >> 16) - 1; }
+
+struct TmShared {
+    int bbox[4];       // x0 min, x0 max, y0 min, y0 max over the recorded in-image cells
+    int max_runs;
+    int overflow;
+};
+
+struct TmGeom {
+    float t1x, t1y, t1z, cx, cy, inv_cx, inv_cy, half_w, half_h;
+};
+
+__device__ __forceinline__ Tap tm_tap(const TmGeom& g, const PixelTerm& pt, float d) {
+    float ix, iy;
+    sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d, g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w, g.half_h, ix, iy);
+    return make_tap(ix, iy);
+}
+
+// 10-term quadratic form of one plane in the Gram matrix of its cell
+__device__ __forceinline__ float tm_quad(const float* G, float fx, float fy) {
+    Tap tap;
+    tap.x0 = 0; tap.y0 = 0; tap.fx = fx; tap.fy = fy;
+    float nw, ne, sw, se;
+    bilinear_weights(tap, nw, ne, sw, se);
+    const float diag = nw * nw * G[0] + ne * ne * G[4] + sw * sw * G[7] + se * se * G[9];
+    const float off = nw * (ne * G[1] + sw * G[2] + se * G[3]) + ne * (sw * G[5] + se * G[6]) + sw * se * G[8];
+    return fmaf(2.0f, off, diag);
+}
+
+// Window does not fit: planes [ka, kb) of one pixel with per-thread gathers from global memory.
+__device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* __restrict__ src,
+                                              const float* __restrict__ refp, const TmGeom& g,
+                                              const PixelTerm& pt, const float* d_s, int ka, int kb,
+                                              float inv_sigma, float* out_col, bool first_view) {
+    const int HW = H * W;
+    int k = ka;
+    while (k < kb) {
+        float ix, iy;
+        sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w, g.half_h, ix, iy);
+        const Tap tap = make_tap(ix, iy);
+        const CellTaps cell = cell_taps(tap, H, W);
+        float q[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) q[i] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float r = __ldg(refp + (long long)c * HW);
+            const float* sc = src + (long long)c * HW;
+            const float e0 = (cell.v00 ? __ldg(sc + cell.o00) : 0.f) - r;
+            const float e1 = (cell.v01 ? __ldg(sc + cell.o01) : 0.f) - r;
+            const float e2 = (cell.v10 ? __ldg(sc + cell.o10) : 0.f) - r;
+            const float e3 = (cell.v11 ? __ldg(sc + cell.o11) : 0.f) - r;
+            q[0] = fmaf(e0, e0, q[0]); q[1] = fmaf(e0, e1, q[1]); q[2] = fmaf(e0, e2, q[2]);
+            q[3] = fmaf(e0, e3, q[3]); q[4] = fmaf(e1, e1, q[4]); q[5] = fmaf(e1, e2, q[5]);
+            q[6] = fmaf(e1, e3, q[6]); q[7] = fmaf(e2, e2, q[7]); q[8] = fmaf(e2, e3, q[8]);
+            q[9] = fmaf(e3, e3, q[9]);
+        }
+        const float cx0 = (float)tap.x0, cy0 = (float)tap.y0;
+        const bool outside = cell.id < 0;
+        float fx = tap.fx, fy = tap.fy;
+        for (;;) {
+            const float val = (outside ? q[0] : tm_quad(q, fx, fy)) * inv_sigma;
+            float* o = out_col + k * TM_OS;
+            *o = first_view ? val : (*o + val);
+            if (++k >= kb) break;
+            sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w, g.half_h, ix, iy);
+            const Tap nt = make_tap(ix, iy);
+            if (outside) {
+                if (cell_taps(nt, H, W).id >= 0) break;
+            } else {
+                fx = ix - cx0; fy = iy - cy0;
+                const bool same = (nt.x0 == tap.x0 && nt.y0 == tap.y0) ||
+                                  (fx >= -kCellSlack && fx <= 1.0f + kCellSlack && fy >= -kCellSlack &&
+                                   fy <= 1.0f + kCellSlack && nt.x0 > -1000000);
+                if (!same) break;
+            }
+        }
+    }
+}
+
+template <int NSLOT>
+__global__ void __launch_bounds__(TM_NT, 5)
+sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map_src,
+                      const __grid_constant__ CUtensorMap map_ref) {
+    __shared__ __align__(128) float stage0[TM_NSTAGE * TM_STAGE];      // TMA destinations
+    __shared__ int cell_s[TM_MAXRUN * TM_PX];                          // [MAXRUN][PX] cell of each run
+    __shared__ short kst_s[(TM_MAXRUN + 1) * TM_PX];                   // [MAXRUN + 1][PX] first plane
+    extern __shared__ __align__(16) float out_s[];                     // [kper][PX + 1] result tile
+    __shared__ unsigned long long full_bar[TM_NSTAGE];
+    __shared__ TmShared ts;
+    __shared__ float lsm_m[TM_PX], lsm_l[TM_PX];
+
+    const int HW = a.H * a.W;
+    const int kper = (a.D + a.PS - 1) / a.PS;
+    float* d_s = out_s + kper * TM_OS;                                 // [kper]
+    const int k0 = blockIdx.y * kper;
+    const int nk = min(a.D, k0 + kper) - k0;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int px = tid >> 2, t = tid & 3;
+    const int tiles_x = (a.W + TM_PX - 1) / TM_PX;
+    const int b = blockIdx.z;
+    const int y = blockIdx.x / tiles_x, tx = blockIdx.x - y * tiles_x;
+    const int x = tx * TM_PX + px;
+    const bool active = x < a.W;
+    const int p = active ? y * a.W + x : y * a.W;
+    if (nk <= 0) return;
+    for (int k = tid; k < nk; k += TM_NT) d_s[k] = __ldg(a.d + k0 + k);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TM_NSTAGE; ++s) tm_mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    const float* rays = a.rays + (long long)b * a.rays_bs;
+    const float rx = __ldg(rays + p), ry = __ldg(rays + HW + p), rz = __ldg(rays + 2 * HW + p);
+    const float* ref = a.ref + (long long)b * a.ref_bs;
+    const int nchunk = (a.C + TM_CK - 1) / TM_CK;
+    const float inv_sigma = __frcp_rn(a.sigma);
+    // planes walked by this lane in the run detection
+    const int kpt = (nk + TM_T - 1) / TM_T;
+    const int wa = min(nk, t * kpt), wb = min(nk, wa + kpt);
+    unsigned q_issue = 0, q_use = 0;   // chunk sequence numbers (stage = q % NSTAGE, parity = q / NSTAGE)
+
+    for (int v = 0; v < a.V; ++v) {
+        const float* src = a.src + (long long)b * a.src_bs + (long long)v * a.src_vs;
+        PixelTerm pt;
+        TmGeom g;
+        {
+            const ViewGeom vg = load_view_geom(a.K + (long long)b * a.k_bs,
+                                               a.pose + (long long)b * a.pose_bs + (long long)v * 16);
+            pt = pixel_term(vg, rx, ry, rz);
+            g.t1x = vg.t1[0]; g.t1y = vg.t1[1]; g.t1z = vg.t1[2]; g.cx = vg.cx; g.cy = vg.cy;
+            g.inv_cx = __frcp_rn(vg.cx); g.inv_cy = __frcp_rn(vg.cy);
+            g.half_w = (float)a.W * 0.5f; g.half_h = (float)a.H * 0.5f;
+        }
+
+        // ---------------- 1. runs of this pixel: each lane walks its quarter of the planes ----
+        if (tid == 0) {
+            ts.bbox[0] = 1 << 30; ts.bbox[1] = -(1 << 30); ts.bbox[2] = 1 << 30; ts.bbox[3] = -(1 << 30);
+            ts.max_runs = 0; ts.overflow = 0;
+        }
+        __syncthreads();   // d_s, barrier init, ts; previous view done with cell_s / kst_s
+        int nrun;          // runs of this pixel (all four lanes agree)
+        {
+            unsigned long long starts = 0ull;
+            int n = 0, first_id = kTmNone, cur_id = kTmNone, cur_x = 0, cur_y = 0;
+            int bx0 = 1 << 30, bx1 = -(1 << 30), by0 = 1 << 30, by1 = -(1 << 30);
+            if (active) {
+                for (int k = wa; k < wb; ++k) {
+                    float ix, iy;
+                    sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w,
+                                     g.half_h, ix, iy);
+                    const Tap tap = make_tap(ix, iy);
+                    const bool inside = (tap.x0 >= -1) & (tap.x0 < a.W) & (tap.y0 >= -1) & (tap.y0 < a.H);
+                    const int id = inside ? tm_pack(tap.x0, tap.y0) : kTmOutside;
+                    bool cont = (id == cur_id);
+                    if (!cont && cur_id >= 0) {   // inside a run with a real cell: border slack
+                        const float fx = ix - (float)cur_x, fy = iy - (float)cur_y;
+                        cont = fx >= -kCellSlack && fx <= 1.0f + kCellSlack && fy >= -kCellSlack &&
+                               fy <= 1.0f + kCellSlack;
+                    }
+                    if (!cont) {
+                        cur_id = id; cur_x = tap.x0; cur_y = tap.y0;
+                        starts |= 1ull << (k - wa);
+                        if (n == 0) first_id = id;
+                        ++n;
+                        if (inside) {
+                            bx0 = min(bx0, tap.x0); bx1 = max(bx1, tap.x0);
+                            by0 = min(by0, tap.y0); by1 = max(by1, tap.y0);
+                        }
+                    }
+                }
+            }
+            // stitch the four lists: my first run continues the previous lane's last run when both
+            // start from the same cell
+            const int prev_last = __shfl_up_sync(0xffffffffu, cur_id, 1, TM_T);
+            const int merge = (t > 0 && n > 0 && first_id == prev_last) ? 1 : 0;
+            const int mine = n - merge;
+            int incl = mine;
+            int up = __shfl_up_sync(0xffffffffu, incl, 1, TM_T);
+            if (t >= 1) incl += up;
+            up = __shfl_up_sync(0xffffffffu, incl, 2, TM_T);
+            if (t >= 2) incl += up;
+            nrun = __shfl_sync(0xffffffffu, incl, TM_T - 1, TM_T);
+            bool over = nrun > TM_MAXRUN;
+            if (active && !over) {
+                int gi = incl - mine - merge;      // global index of my first local run
+                unsigned long long m = starts;
+                while (m) {
+                    const int i = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if (gi >= incl - mine) {       // not the merged one
+                        const int k = wa + i;
+                        const Tap tap = tm_tap(g, pt, d_s[k]);
+                        const bool inside = (tap.x0 >= -1) & (tap.x0 < a.W) & (tap.y0 >= -1) & (tap.y0 < a.H);
+                        cell_s[gi * TM_PX + px] = inside ? tm_pack(tap.x0, tap.y0) : kTmOutside;
+                        kst_s[gi * TM_PX + px] = (short)k;
+                    }
+                    ++gi;
+                }
+                if (wb == nk && wa < wb) kst_s[nrun * TM_PX + px] = (short)nk;
+            }
+            bx0 = __reduce_min_sync(0xffffffffu, bx0); bx1 = __reduce_max_sync(0xffffffffu, bx1);
+            by0 = __reduce_min_sync(0xffffffffu, by0); by1 = __reduce_max_sync(0xffffffffu, by1);
+            const int mr = __reduce_max_sync(0xffffffffu, active ? nrun : 0);
+            const int ov = __any_sync(0xffffffffu, active && over);
+            if (lane == 0) {
+                atomicMin(&ts.bbox[0], bx0); atomicMax(&ts.bbox[1], bx1);
+                atomicMin(&ts.bbox[2], by0); atomicMax(&ts.bbox[3], by1);
+                atomicMax(&ts.max_runs, mr);
+                if (ov) atomicOr(&ts.overflow, 1);
+            }
+        }
+        __syncthreads();
+        // TMA needs every box row to start on a 16-byte boundary of global memory (an unaligned
+        // innermost coordinate raises "illegal instruction", tools/probe/tma_probe.cu): the window
+        // starts at a multiple of 4 columns (W % 4 == 0, so rows keep that alignment)
+        int wx0 = ts.bbox[0] & ~3, wy0 = ts.bbox[2];
+        int ww = ts.bbox[1] + 2 - wx0, wh = ts.bbox[3] + 2 - wy0;   // taps reach x0 + 1, y0 + 1
+        if (ts.bbox[1] < ts.bbox[0]) { wx0 = 0; wy0 = 0; ww = 0; wh = 0; }   // every cell outside
+        const bool fits = (ww <= TM_WC) && (wh <= TM_WR) && !ts.overflow;
+        const int max_runs = ts.max_runs;
+        __syncthreads();   // ts is re-initialised by thread 0 at the top of the next view
+
+        if (!fits) {
+            if (active && wa < wb)
+                tm_gather_planes(a.C, a.H, a.W, src, ref + p, g, pt, d_s, wa, wb, inv_sigma, out_s + px, v == 0);
+            continue;   // next view (uniform across the CTA)
+        }
+
+        // ---------------- 2-4. passes of TM_T * NSLOT runs ----------------------------------
+        for (int first = 0; first < max_runs; first += TM_T * NSLOT) {
+            float G[NSLOT][10];
+            int coff[NSLOT];   // window offset of the run's cell; runs whose cell is outside the image
+                               // accumulate from offset 0 and are evaluated from rr instead
+            float rr = 0.f;    // sum_c ref^2: the cost of a plane with no tap inside the image
+            int nloc = 0;
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) {
+#pragma unroll
+                for (int i = 0; i < 10; ++i) G[j][i] = 0.f;
+                coff[j] = 0;
+                const int run = first + t + TM_T * j;
+                if (active && run < nrun) {
+                    nloc = j + 1;
+                    const int pc = cell_s[run * TM_PX + px];
+                    if (pc != kTmOutside) coff[j] = (tm_cell_y(pc) - wy0) * TM_ROW + (tm_cell_x(pc) - wx0);
+                }
+            }
+
+            auto issue = [&](int chunk) {
+                const int s = q_issue % TM_NSTAGE;
+                ++q_issue;
+                float* st = stage0 + s * TM_STAGE;
+                tm_mbar_expect_tx(&full_bar[s], (unsigned)((wh * TM_ROW + TM_CK * TM_PX) * sizeof(float)));
+                for (int r = 0; r < wh; ++r)
+                    tm_load_5d(st + r * TM_ROW, &map_src, wx0, wy0 + r, chunk * TM_CK, v, b, &full_bar[s]);
+                tm_load_4d(st + TM_WIN, &map_ref, tx * TM_PX, y, chunk * TM_CK, b, &full_bar[s]);
+            };
+            if (tid == 0) {
+                for (int c = 0; c < min(TM_NSTAGE, nchunk); ++c) issue(c);
+            }
+            for (int chunk = 0; chunk < nchunk; ++chunk) {
+                const int s = q_use % TM_NSTAGE;
+                tm_mbar_wait(&full_bar[s], (q_use / TM_NSTAGE) & 1);
+                ++q_use;
+                const float* st = stage0 + s * TM_STAGE;
+                const int nc = min(TM_CK, a.C - chunk * TM_CK);
+                if (nc == TM_CK) {
+                    float r[TM_CK];
+#pragma unroll
+                    for (int c = 0; c < TM_CK; ++c) {
+                        r[c] = st[TM_WIN + c * TM_PX + px];
+                        rr = fmaf(r[c], r[c], rr);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NSLOT; ++j) {
+                        if (j < nloc) {
+                            const float* w = st + coff[j];
+#pragma unroll
+                            for (int c = 0; c < TM_CK; ++c) {
+                                const float e0 = w[c * TM_WC] - r[c];
+                                const float e1 = w[c * TM_WC + 1] - r[c];
+                                const float e2 = w[c * TM_WC + TM_ROW] - r[c];
+                                const float e3 = w[c * TM_WC + TM_ROW + 1] - r[c];
+                                G[j][0] = fmaf(e0, e0, G[j][0]); G[j][1] = fmaf(e0, e1, G[j][1]);
+                                G[j][2] = fmaf(e0, e2, G[j][2]); G[j][3] = fmaf(e0, e3, G[j][3]);
+                                G[j][4] = fmaf(e1, e1, G[j][4]); G[j][5] = fmaf(e1, e2, G[j][5]);
+                                G[j][6] = fmaf(e1, e3, G[j][6]); G[j][7] = fmaf(e2, e2, G[j][7]);
+                                G[j][8] = fmaf(e2, e3, G[j][8]); G[j][9] = fmaf(e3, e3, G[j][9]);
+                            }
+                        }
+                    }
+                } else {
+                    // last, partial chunk: only the channels that exist
+                    for (int c = 0; c < nc; ++c) {
+                        const float rc = st[TM_WIN + c * TM_PX + px];
+                        rr = fmaf(rc, rc, rr);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NSLOT; ++j) {
+                        if (j < nloc) {
+                            const float* w = st + coff[j];
+#pragma unroll 1
+                            for (int c = 0; c < nc; ++c) {
+                                const float rc = st[TM_WIN + c * TM_PX + px];
+                                const float e0 = w[c * TM_WC] - rc;
+                                const float e1 = w[c * TM_WC + 1] - rc;
+                                const float e2 = w[c * TM_WC + TM_ROW] - rc;
+                                const float e3 = w[c * TM_WC + TM_ROW + 1] - rc;
+                                G[j][0] = fmaf(e0, e0, G[j][0]); G[j][1] = fmaf(e0, e1, G[j][1]);
+                                G[j][2] = fmaf(e0, e2, G[j][2]); G[j][3] = fmaf(e0, e3, G[j][3]);
+                                G[j][4] = fmaf(e1, e1, G[j][4]); G[j][5] = fmaf(e1, e2, G[j][5]);
+                                G[j][6] = fmaf(e1, e3, G[j][6]); G[j][7] = fmaf(e2, e2, G[j][7]);
+                                G[j][8] = fmaf(e2, e3, G[j][8]); G[j][9] = fmaf(e3, e3, G[j][9]);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();   // every lane is done with this stage
+                if (tid == 0 && chunk + TM_NSTAGE < nchunk) issue(chunk + TM_NSTAGE);
+            }
+
+            // ---------------- 4. planes of each of my runs -> result tile ---------------------
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) {
+                if (j < nloc) {
+                    const int run = first + t + TM_T * j;
+                    const int pc = cell_s[run * TM_PX + px];
+                    const int ka = kst_s[run * TM_PX + px], kb = kst_s[(run + 1) * TM_PX + px];
+                    const float fx0 = (float)tm_cell_x(pc), fy0 = (float)tm_cell_y(pc);
+                    for (int k = ka; k < kb; ++k) {
+                        float val;
+                        if (pc == kTmOutside) {
+                            val = rr;
+                        } else {
+                            float ix, iy;
+                            sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy,
+                                             g.half_w, g.half_h, ix, iy);
+                            val = tm_quad(G[j], ix - fx0, iy - fy0);
+                        }
+                        val *= inv_sigma;
+                        float* o = out_s + k * TM_OS + px;
+                        *o = (v == 0) ? val : (*o + val);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---------------- 5. result tile -> global memory, one 128-byte row per warp-instruction ----
+    __syncthreads();
+    if (a.lsm != nullptr) {   // log_softmax over the planes (host guarantees PS == 1)
+        float m = -INFINITY;
+        for (int k = t; k < nk; k += TM_T) m = fmaxf(m, out_s[k * TM_OS + px]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        float s = 0.f;
+        for (int k = t; k < nk; k += TM_T) s += expf(out_s[k * TM_OS + px] - m);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (t == 0) { lsm_m[px] = m; lsm_l[px] = logf(s); }
+        __syncthreads();
+    }
+    {
+        const int col = tid & 31, x_out = tx * TM_PX + col;
+        if (x_out < a.W) {
+            const long long base = ((long long)b * a.D + k0) * HW + (long long)y * a.W + x_out;
+            for (int k = tid >> 5; k < nk; k += TM_NT / 32) {
+                const float val = out_s[k * TM_OS + col];
+                a.cost[base + (long long)k * HW] = val;
+                if (a.lsm != nullptr) a.lsm[base + (long long)k * HW] = (val - lsm_m[col]) - lsm_l[col];
+            }
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*tm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+static tm_encode_fn tm_encoder() {
+    static tm_encode_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (tm_encode_fn)f;
+    }();
+    return fn;
+}
+
+static size_t tm_smem_bytes(int kper) {
+    // dynamic part only: result tile + plane depths (stages and run tables are static, ~33 KB)
+    const size_t n = (size_t)kper * TM_OS * sizeof(float) + (size_t)kper * sizeof(float);
+    return (n + 15) & ~(size_t)15;
+}
+
+// Can the TMA kernel take this call?  (16-byte aligned bases and strides, plane block small enough
+// for the 64-bit run-start mask.)
+bool sweep_gram_tma_supported(const SweepArgs& a) {
+    const int kper = (a.D + a.PS - 1) / a.PS;
+    if (a.W % 4 != 0 || kper > 4 * 64 || a.W >= 32767 || a.H >= 32767) return false;
+    if (((uintptr_t)a.ref | (uintptr_t)a.src) & 15) return false;
+    if ((a.ref_bs | a.src_bs | a.src_vs) & 3) return false;
+    if (a.ref_bs < 0 || a.src_bs < 0 || a.src_vs < 0) return false;
+    if (a.B > 1 && (a.ref_bs == 0 || a.src_bs == 0)) return false;
+    if (a.V > 1 && a.src_vs == 0) return false;
+    if (tm_smem_bytes(kper) > 160 * 1024) return false;
+    return tm_encoder() != nullptr;
+}
+
+int launch_sweep_gram_tma(const SweepArgs& a, cudaStream_t st) {
+    static const int nslot = [] { const char* e = getenv("DPV_SWEEP_TMA_NSLOT"); return e ? atoi(e) : 0; }();
+    if (!sweep_gram_tma_supported(a)) return DPV_E_UNSUPP;
+    tm_encode_fn enc = tm_encoder();
+    const int kper = (a.D + a.PS - 1) / a.PS;
+    const cuuint64_t chw = (cuuint64_t)a.C * a.H * a.W;
+    CUtensorMap msrc, mref;
+    {
+        const cuuint64_t vs = a.V > 1 ? (cuuint64_t)a.src_vs : chw;
+        const cuuint64_t bs = a.B > 1 ? (cuuint64_t)a.src_bs : vs * a.V;
+        const cuuint64_t gdim[5] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.V, (cuuint64_t)a.B};
+        const cuuint64_t gstr[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4, vs * 4, bs * 4};
+        const cuuint32_t box[5] = {TM_WC, 1, TM_CK, 1, 1};
+        const cuuint32_t est[5] = {1, 1, 1, 1, 1};
+        if (enc(&msrc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(a.src), gdim, gstr, box, est,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return DPV_E_UNSUPP;
+    }
+    {
+        const cuuint64_t bs = a.B > 1 ? (cuuint64_t)a.ref_bs : chw;
+        const cuuint64_t gdim[4] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4, bs * 4};
+        const cuuint32_t box[4] = {TM_PX, 1, TM_CK, 1};
+        const cuuint32_t est[4] = {1, 1, 1, 1};
+        if (enc(&mref, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.ref), gdim, gstr, box, est,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return DPV_E_UNSUPP;
+    }
+    const size_t smem = tm_smem_bytes(kper);
+    const int tiles = ((a.W + TM_PX - 1) / TM_PX) * a.H;
+    dim3 grid(tiles, a.PS, a.B), block(TM_NT);
+    cudaError_t e;
+    if (nslot == 3) {
+        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        sweep_gram_tma_kernel<3><<<grid, block, smem, st>>>(a, msrc, mref);
+    } else {
+        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        sweep_gram_tma_kernel<4><<<grid, block, smem, st>>>(a, msrc, mref);
+    }
+    DPV_LAUNCH_END();
+    return 0;
+}
+
+}  // namespace dpv

@@ -50,9 +50,11 @@ def cam_dict(c):
 
 # ------------------------------------------------------------------------- K1 + K2a
 @pytest.mark.parametrize("name", cases.SWEEP_CASES)
-@pytest.mark.parametrize("dist,algo", [("L2", 3), ("L2", 2), ("L2", 1), ("L1", 1)])
+@pytest.mark.parametrize("dist,algo", [("L2", 0), ("L2", 4), ("L2", 3), ("L2", 2), ("L2", 1), ("L1", 1)])
 def test_sweep_vs_golden(dpv, golden, name, dist, algo):
     g = golden("sweep")
+    if algo == 4 and cases.sweep_case(name)["w"] % 4 != 0:
+        pytest.skip("the TMA kernel needs 16-byte row strides; algo=0 falls back (covered above)")
     key = "%s_%s" % (name, dist)
     c = cases.sweep_case(name)
     if key in g.files:
@@ -107,6 +109,40 @@ def test_sweep_batched_strided_and_fused_softmax(dpv):
         logclose(lsm[b:b + 1], O.log_softmax_bins(want).numpy())
 
 
+@pytest.mark.parametrize("kind", ["wide_baseline", "many_runs", "tall_motion", "two_views_strided"])
+def test_sweep_tma_window_and_pass_edges(dpv, kind):
+    """The TMA kernel's edge paths against the oracle: a source window wider than its 48-column
+    capacity (per-thread gather fallback), more runs per pixel than one pass holds (16), a window
+    taller than 8 rows, and two views read through a strided [B, V+1, C, h, w] allocation."""
+    synth = dpv.synth
+    if kind == "wide_baseline":      # disparity 6..50 px: window > 48 columns
+        C, h, w, D, B = 9, 8, 128, 32, 2
+        pose = [synth.pose(None, (-2.2, 0.0, 0.0))]
+    elif kind == "many_runs":        # ~24 cells per pixel, window fits
+        C, h, w, D, B = 11, 8, 16, 64, 1
+        pose = [synth.pose(None, (-7.0, 0.0, 0.0))]
+    elif kind == "tall_motion":      # vertical parallax: > 8 window rows
+        C, h, w, D, B = 7, 48, 32, 32, 1
+        pose = [synth.pose(None, (0.0, -1.5, 0.0))]
+    else:
+        C, h, w, D, B = 67, 16, 24, 64, 3
+        pose = [synth.pose(synth.yaw_matrix(0.7), (0.05, -0.02, 0.8)),
+                synth.pose(synth.yaw_matrix(-1.0), (-0.1, 0.03, -0.6))]
+    V = len(pose)
+    d = synth.depth_candidates(5, 40, D)
+    feats = synth.randn(91, B, V + 1, C, h, w)
+    poses = np.stack([np.stack(pose + [synth.pose()])] * B).astype(np.float32)
+    cam = synth.camera(w, h, B)
+    f, p = cu(feats), cu(poses)
+    cost = dpv.ops.sweep_cost_volume(f[:, -1], f[:, :-1], p[:, :-1], cu(cam["intrinsics"]),
+                                     cu(cam["unit_ray"]), d, 10.0, algo=4)
+    for b in range(B):
+        want = O.plane_sweep_cost(T(feats[b:b + 1, -1]), T(feats[b:b + 1, :-1]), d,
+                                  T(poses[b, :-1, :3, :3]), T(poses[b, :-1, :3, 3]),
+                                  T(cam["intrinsics"][b]), T(cam["unit_ray"][b]), 10.0, "L2")
+        close(cost[b:b + 1], want.numpy())
+
+
 def test_sweep_identity_pose_is_near_zero(dpv):
     """Size-independent property at the model's shape: source == reference under the identity
     pose gives a cost volume that is ~0 (only coordinate rounding, SURVEY.md 7 'bit-level')."""
@@ -115,7 +151,7 @@ def test_sweep_identity_pose_is_near_zero(dpv):
     ref = synth.randn(5, 1, C, h, w)
     poses = synth.pose()[None, None]
     cam = synth.camera(w, h, 1)
-    for algo in (1, 2, 3):
+    for algo in (1, 2, 3, 4):
         cost = dpv.ops.sweep_cost_volume(cu(ref), cu(ref[:, None]), cu(poses), cu(cam["intrinsics"]),
                                          cu(cam["unit_ray"]), synth.depth_candidates(5, 40, D), 10.0,
                                          algo=algo)

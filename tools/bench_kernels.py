@@ -88,7 +88,7 @@ def main():
     nrot = 3
     if want("sweep"):
         feats = [torch.randn((B, V + 1, C, h, w), device="cuda") for _ in range(nrot)]
-        for algo in (3, 2, 1):
+        for algo in (4, 3, 2, 1):
             f = lambda i: ops.sweep_cost_volume(feats[i][:, -1], feats[i][:, :-1], poses[:, :-1], K, rays, d, 10.0, algo=algo)
             med, best = timeit(f, nrot, iters=10 if algo == 1 else 20)
             byt = B * (4 * h * w * (C * (1 + V) + D) + 12 * h * w)
