@@ -76,6 +76,26 @@ __device__ __forceinline__ int tm_pack(int x0, int y0) { return ((y0 + 1) << 16)
 __device__ __forceinline__ int tm_cell_x(int p) { return (p & 0xffff) - 1; }
 __device__ __forceinline__ int tm_cell_y(int p) { return (p >> 16) - 1; }
 
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100a): two runs of a lane share every
+// instruction of the Gram update, halving the issue slots and fma-pipe cycles of the hot loop.
+typedef unsigned long long tm_f2;
+__device__ __forceinline__ tm_f2 tm_pk(float lo, float hi) {
+    tm_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void tm_upk(tm_f2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ tm_f2 tm_sub2(tm_f2 a, tm_f2 b) {
+    tm_f2 r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void tm_fma2(tm_f2& acc, tm_f2 a, tm_f2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 struct TmShared {
     int bbox[4];       // x0 min, x0 max, y0 min, y0 max over the recorded in-image cells
     int max_runs;
@@ -86,9 +106,22 @@ struct TmGeom {
     float t1x, t1y, t1z, cx, cy, inv_cx, inv_cy, half_w, half_h;
 };
 
+// sweep_coord_fast with the reciprocal on the SFU (MUFU.RCP, ~1 ulp; the IEEE __frcp_rn expands
+// to ~10 instructions and was 6 % of the kernel).  Every phase uses this one function, so a plane
+// gets the same coordinate wherever it is recomputed.
+__device__ __forceinline__ void tm_coord(const TmGeom& g, const PixelTerm& p, float d, float& ix, float& iy) {
+    const float px = fmaf(p.x, d, g.t1x);
+    const float py = fmaf(p.y, d, g.t1y);
+    const float pz = fmaf(p.z, d, g.t1z);
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(pz + 1e-10f));
+    const float u = px * inv, v = py * inv;
+    ix = fmaf(fmaf(u - g.cx, g.inv_cx, 1.0f), g.half_w, -0.5f);
+    iy = fmaf(fmaf(v - g.cy, g.inv_cy, 1.0f), g.half_h, -0.5f);
+}
 __device__ __forceinline__ Tap tm_tap(const TmGeom& g, const PixelTerm& pt, float d) {
     float ix, iy;
-    sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d, g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w, g.half_h, ix, iy);
+    tm_coord(g, pt, d, ix, iy);
     return make_tap(ix, iy);
 }
 
@@ -112,7 +145,7 @@ __device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* 
     int k = ka;
     while (k < kb) {
         float ix, iy;
-        sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w, g.half_h, ix, iy);
+        tm_coord(g, pt, d_s[k], ix, iy);
         const Tap tap = make_tap(ix, iy);
         const CellTaps cell = cell_taps(tap, H, W);
         float q[10];
@@ -138,7 +171,7 @@ __device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* 
             float* o = out_col + k * TM_OS;
             *o = first_view ? val : (*o + val);
             if (++k >= kb) break;
-            sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w, g.half_h, ix, iy);
+            tm_coord(g, pt, d_s[k], ix, iy);
             const Tap nt = make_tap(ix, iy);
             if (outside) {
                 if (cell_taps(nt, H, W).id >= 0) break;
@@ -216,6 +249,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
         }
         __syncthreads();   // d_s, barrier init, ts; previous view done with cell_s / kst_s
         int nrun;          // runs of this pixel (all four lanes agree)
+        int my_run0;       // run that holds my first plane
         {
             unsigned long long starts = 0ull;
             int n = 0, first_id = kTmNone, cur_id = kTmNone, cur_x = 0, cur_y = 0;
@@ -223,8 +257,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
             if (active) {
                 for (int k = wa; k < wb; ++k) {
                     float ix, iy;
-                    sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy, g.half_w,
-                                     g.half_h, ix, iy);
+                    tm_coord(g, pt, d_s[k], ix, iy);
                     const Tap tap = make_tap(ix, iy);
                     const bool inside = (tap.x0 >= -1) & (tap.x0 < a.W) & (tap.y0 >= -1) & (tap.y0 < a.H);
                     const int id = inside ? tm_pack(tap.x0, tap.y0) : kTmOutside;
@@ -257,6 +290,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
             up = __shfl_up_sync(0xffffffffu, incl, 2, TM_T);
             if (t >= 2) incl += up;
             nrun = __shfl_sync(0xffffffffu, incl, TM_T - 1, TM_T);
+            my_run0 = incl - mine - merge;
             bool over = nrun > TM_MAXRUN;
             if (active && !over) {
                 int gi = incl - mine - merge;      // global index of my first local run
@@ -305,15 +339,18 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
 
         // ---------------- 2-4. passes of TM_T * NSLOT runs ----------------------------------
         for (int first = 0; first < max_runs; first += TM_T * NSLOT) {
-            float G[NSLOT][10];
+            static_assert(NSLOT % 2 == 0, "runs are accumulated in fp32x2 pairs");
+            tm_f2 G2[NSLOT / 2][10];   // Gram matrices of slots (2q, 2q+1) in the (lo, hi) halves
             int coff[NSLOT];   // window offset of the run's cell; runs whose cell is outside the image
                                // accumulate from offset 0 and are evaluated from rr instead
             float rr = 0.f;    // sum_c ref^2: the cost of a plane with no tap inside the image
             int nloc = 0;
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j) {
+                if ((j & 1) == 0) {
 #pragma unroll
-                for (int i = 0; i < 10; ++i) G[j][i] = 0.f;
+                    for (int i = 0; i < 10; ++i) G2[j / 2][i] = 0ull;
+                }
                 coff[j] = 0;
                 const int run = first + t + TM_T * j;
                 if (active && run < nrun) {
@@ -349,20 +386,21 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                         rr = fmaf(r[c], r[c], rr);
                     }
 #pragma unroll
-                    for (int j = 0; j < NSLOT; ++j) {
-                        if (j < nloc) {
-                            const float* w = st + coff[j];
+                    for (int q = 0; q < NSLOT / 2; ++q) {
+                        if (2 * q < nloc) {
+                            const float* wa_ = st + coff[2 * q];
+                            const float* wb_ = st + coff[2 * q + 1];
 #pragma unroll
                             for (int c = 0; c < TM_CK; ++c) {
-                                const float e0 = w[c * TM_WC] - r[c];
-                                const float e1 = w[c * TM_WC + 1] - r[c];
-                                const float e2 = w[c * TM_WC + TM_ROW] - r[c];
-                                const float e3 = w[c * TM_WC + TM_ROW + 1] - r[c];
-                                G[j][0] = fmaf(e0, e0, G[j][0]); G[j][1] = fmaf(e0, e1, G[j][1]);
-                                G[j][2] = fmaf(e0, e2, G[j][2]); G[j][3] = fmaf(e0, e3, G[j][3]);
-                                G[j][4] = fmaf(e1, e1, G[j][4]); G[j][5] = fmaf(e1, e2, G[j][5]);
-                                G[j][6] = fmaf(e1, e3, G[j][6]); G[j][7] = fmaf(e2, e2, G[j][7]);
-                                G[j][8] = fmaf(e2, e3, G[j][8]); G[j][9] = fmaf(e3, e3, G[j][9]);
+                                const tm_f2 R = tm_pk(r[c], r[c]);
+                                const tm_f2 e0 = tm_sub2(tm_pk(wa_[c * TM_WC], wb_[c * TM_WC]), R);
+                                const tm_f2 e1 = tm_sub2(tm_pk(wa_[c * TM_WC + 1], wb_[c * TM_WC + 1]), R);
+                                const tm_f2 e2 = tm_sub2(tm_pk(wa_[c * TM_WC + TM_ROW], wb_[c * TM_WC + TM_ROW]), R);
+                                const tm_f2 e3 = tm_sub2(tm_pk(wa_[c * TM_WC + TM_ROW + 1], wb_[c * TM_WC + TM_ROW + 1]), R);
+                                tm_fma2(G2[q][0], e0, e0); tm_fma2(G2[q][1], e0, e1); tm_fma2(G2[q][2], e0, e2);
+                                tm_fma2(G2[q][3], e0, e3); tm_fma2(G2[q][4], e1, e1); tm_fma2(G2[q][5], e1, e2);
+                                tm_fma2(G2[q][6], e1, e3); tm_fma2(G2[q][7], e2, e2); tm_fma2(G2[q][8], e2, e3);
+                                tm_fma2(G2[q][9], e3, e3);
                             }
                         }
                     }
@@ -373,21 +411,22 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                         rr = fmaf(rc, rc, rr);
                     }
 #pragma unroll
-                    for (int j = 0; j < NSLOT; ++j) {
-                        if (j < nloc) {
-                            const float* w = st + coff[j];
+                    for (int q = 0; q < NSLOT / 2; ++q) {
+                        if (2 * q < nloc) {
+                            const float* wa_ = st + coff[2 * q];
+                            const float* wb_ = st + coff[2 * q + 1];
 #pragma unroll 1
                             for (int c = 0; c < nc; ++c) {
                                 const float rc = st[TM_WIN + c * TM_PX + px];
-                                const float e0 = w[c * TM_WC] - rc;
-                                const float e1 = w[c * TM_WC + 1] - rc;
-                                const float e2 = w[c * TM_WC + TM_ROW] - rc;
-                                const float e3 = w[c * TM_WC + TM_ROW + 1] - rc;
-                                G[j][0] = fmaf(e0, e0, G[j][0]); G[j][1] = fmaf(e0, e1, G[j][1]);
-                                G[j][2] = fmaf(e0, e2, G[j][2]); G[j][3] = fmaf(e0, e3, G[j][3]);
-                                G[j][4] = fmaf(e1, e1, G[j][4]); G[j][5] = fmaf(e1, e2, G[j][5]);
-                                G[j][6] = fmaf(e1, e3, G[j][6]); G[j][7] = fmaf(e2, e2, G[j][7]);
-                                G[j][8] = fmaf(e2, e3, G[j][8]); G[j][9] = fmaf(e3, e3, G[j][9]);
+                                const tm_f2 R = tm_pk(rc, rc);
+                                const tm_f2 e0 = tm_sub2(tm_pk(wa_[c * TM_WC], wb_[c * TM_WC]), R);
+                                const tm_f2 e1 = tm_sub2(tm_pk(wa_[c * TM_WC + 1], wb_[c * TM_WC + 1]), R);
+                                const tm_f2 e2 = tm_sub2(tm_pk(wa_[c * TM_WC + TM_ROW], wb_[c * TM_WC + TM_ROW]), R);
+                                const tm_f2 e3 = tm_sub2(tm_pk(wa_[c * TM_WC + TM_ROW + 1], wb_[c * TM_WC + TM_ROW + 1]), R);
+                                tm_fma2(G2[q][0], e0, e0); tm_fma2(G2[q][1], e0, e1); tm_fma2(G2[q][2], e0, e2);
+                                tm_fma2(G2[q][3], e0, e3); tm_fma2(G2[q][4], e1, e1); tm_fma2(G2[q][5], e1, e2);
+                                tm_fma2(G2[q][6], e1, e3); tm_fma2(G2[q][7], e2, e2); tm_fma2(G2[q][8], e2, e3);
+                                tm_fma2(G2[q][9], e3, e3);
                             }
                         }
                     }
@@ -396,30 +435,62 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                 if (tid == 0 && chunk + TM_NSTAGE < nchunk) issue(chunk + TM_NSTAGE);
             }
 
-            // ---------------- 4. planes of each of my runs -> result tile ---------------------
+            // ---------------- 4. planes -> result tile ------------------------------------------
+            // The Gram matrices go through shared memory (the stage buffers are idle now) so that
+            // every lane evaluates an equal share of the planes -- its own quarter, the same planes
+            // it walked in step 1 -- whichever lane accumulated their run.  (Evaluating "the planes
+            // of my runs" instead leaves most lanes idle while one works through a 25-plane run.)
+            float* Gs = stage0;   // [run - first][10][PX], run stride padded by 8 floats (banks)
+            constexpr int GS_RUN = 10 * TM_PX + 8;
+            static_assert(TM_T * NSLOT * GS_RUN <= TM_NSTAGE * TM_STAGE, "Gram exchange fits in the stages");
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j) {
                 if (j < nloc) {
-                    const int run = first + t + TM_T * j;
-                    const int pc = cell_s[run * TM_PX + px];
-                    const int ka = kst_s[run * TM_PX + px], kb = kst_s[(run + 1) * TM_PX + px];
-                    const float fx0 = (float)tm_cell_x(pc), fy0 = (float)tm_cell_y(pc);
-                    for (int k = ka; k < kb; ++k) {
-                        float val;
-                        if (pc == kTmOutside) {
-                            val = rr;
-                        } else {
-                            float ix, iy;
-                            sweep_coord_fast(g.t1x, g.t1y, g.t1z, pt, d_s[k], g.cx, g.cy, g.inv_cx, g.inv_cy,
-                                             g.half_w, g.half_h, ix, iy);
-                            val = tm_quad(G[j], ix - fx0, iy - fy0);
-                        }
-                        val *= inv_sigma;
-                        float* o = out_s + k * TM_OS + px;
-                        *o = (v == 0) ? val : (*o + val);
+                    float* gdst = Gs + (t + TM_T * j) * GS_RUN + px;
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) {
+                        float lo, hi;
+                        tm_upk(G2[j / 2][i], lo, hi);
+                        gdst[i * TM_PX] = (j & 1) ? hi : lo;
                     }
                 }
             }
+            __syncthreads();
+            if (active) {
+                const int last = min(first + TM_T * NSLOT, nrun);   // runs [first, last) are in Gs
+                int k = max(wa, (int)kst_s[first * TM_PX + px]);
+                const int kend = min(wb, (int)kst_s[last * TM_PX + px]);
+                int run = max(my_run0, first);
+                int knext = k;    // first plane of the run after `run`; forces a load on entry
+                float gq[10];
+                float fx0 = 0.f, fy0 = 0.f;
+                bool outside = true;
+                --run;
+                for (; k < kend; ++k) {
+                    if (k >= knext) {
+                        do {
+                            ++run;
+                            knext = kst_s[(run + 1) * TM_PX + px];
+                        } while (k >= knext);
+                        const int pc = cell_s[run * TM_PX + px];
+                        outside = (pc == kTmOutside);
+                        fx0 = (float)tm_cell_x(pc); fy0 = (float)tm_cell_y(pc);
+                        const float* gsrc = Gs + (run - first) * GS_RUN + px;
+#pragma unroll
+                        for (int i = 0; i < 10; ++i) gq[i] = gsrc[i * TM_PX];
+                    }
+                    float val = rr;
+                    if (!outside) {
+                        float ix, iy;
+                        tm_coord(g, pt, d_s[k], ix, iy);
+                        val = tm_quad(gq, ix - fx0, iy - fy0);
+                    }
+                    val *= inv_sigma;
+                    float* o = out_s + k * TM_OS + px;
+                    *o = (v == 0) ? val : (*o + val);
+                }
+            }
+            __syncthreads();   // Gs (= the stages) is free again for the next pass / view
         }
     }
 
@@ -521,10 +592,10 @@ int launch_sweep_gram_tma(const SweepArgs& a, cudaStream_t st) {
     const int tiles = ((a.W + TM_PX - 1) / TM_PX) * a.H;
     dim3 grid(tiles, a.PS, a.B), block(TM_NT);
     cudaError_t e;
-    if (nslot == 3) {
-        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (nslot == 2) {
+        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        sweep_gram_tma_kernel<3><<<grid, block, smem, st>>>(a, msrc, mref);
+        sweep_gram_tma_kernel<2><<<grid, block, smem, st>>>(a, msrc, mref);
     } else {
         e = cudaFuncSetAttribute(sweep_gram_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
