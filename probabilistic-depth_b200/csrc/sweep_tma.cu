@@ -7,11 +7,14 @@
 // run is a 10-term quadratic form in its bilinear weights.  What changed is the mapping onto the
 // machine (ncu on the tiled kernel, profiles/r01_*: one thread per pixel gives 10 warps per SM at
 // the model's 8 x 64 x 96 pixels, and a quarter of its instructions were 4-byte cp.async copies):
-//   * a CTA owns one row segment of 32 reference pixels, FOUR adjacent lanes per pixel.  The
-//     lanes split the planes for run detection (each walks D/4 planes, the run lists are stitched
-//     with two warp shuffles), split the runs round-robin for the Gram accumulation (NSLOT
-//     Gram matrices of 10 registers per lane instead of 6 x 10 per thread) and evaluate the planes
-//     of their own runs.  4x the threads at ~half the registers: 24 warps per SM instead of 10.
+//   * a CTA owns one row segment of 32 reference pixels with FOUR threads per pixel: lane = pixel,
+//     warp = quarter.  The warps split the planes for run detection (each walks D/4 planes of its
+//     32 pixels; the four run lists of a pixel are stitched through shared memory), split the runs
+//     round-robin for the Gram accumulation (NSLOT Gram matrices per thread instead of 6, updated
+//     two at a time with fp32x2 FFMA2), exchange the matrices through shared memory and evaluate
+//     the planes of their own quarter.  Lanes of a warp do the same job on neighbouring pixels, so
+//     run boundaries and trip counts are (nearly) warp-uniform.  4x the threads at fewer registers:
+//     20 warps per SM instead of 10.
 //   * the source window of the tile and the reference pixels are fetched by the TMA engine
 //     (cp.async.bulk.tensor, 5-D / 4-D maps over the caller's strided [B,V,C,H,W] / [B,C,H,W]
 //     tensors): one elected thread issues one box per window row and chunk of 8 channels,
@@ -37,7 +40,7 @@ constexpr int TM_MAXRUN = 32;                    // runs recorded per pixel and 
 constexpr int TM_ROW = TM_CK * TM_WC;            // floats of one window row (all channels of a chunk)
 constexpr int TM_WIN = TM_WR * TM_ROW;
 constexpr int TM_STAGE = TM_WIN + TM_CK * TM_PX; // + the reference pixels of the chunk
-constexpr int TM_OS = TM_PX + 1;                 // row stride of the result tile (bank spread)
+constexpr int TM_OS = TM_PX;                     // row stride of the result tile (lane = pixel = bank)
 constexpr int kTmOutside = -1;                   // cell id of "no tap inside the image"
 constexpr int kTmNone = -2;
 
@@ -193,7 +196,8 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
     __shared__ __align__(128) float stage0[TM_NSTAGE * TM_STAGE];      // TMA destinations
     __shared__ int cell_s[TM_MAXRUN * TM_PX];                          // [MAXRUN][PX] cell of each run
     __shared__ short kst_s[(TM_MAXRUN + 1) * TM_PX];                   // [MAXRUN + 1][PX] first plane
-    extern __shared__ __align__(16) float out_s[];                     // [kper][PX + 1] result tile
+    extern __shared__ __align__(16) float out_s[];                     // [kper][PX] result tile
+    __shared__ int st_n[TM_T * TM_PX], st_first[TM_T * TM_PX], st_last[TM_T * TM_PX];   // run-list stitching
     __shared__ unsigned long long full_bar[TM_NSTAGE];
     __shared__ TmShared ts;
     __shared__ float lsm_m[TM_PX], lsm_l[TM_PX];
@@ -204,7 +208,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
     const int k0 = blockIdx.y * kper;
     const int nk = min(a.D, k0 + kper) - k0;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int px = tid >> 2, t = tid & 3;
+    const int px = tid & 31, t = tid >> 5;   // lane = pixel, warp = plane quarter / run residue
     const int tiles_x = (a.W + TM_PX - 1) / TM_PX;
     const int b = blockIdx.z;
     const int y = blockIdx.x / tiles_x, tx = blockIdx.x - y * tiles_x;
@@ -279,17 +283,19 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                     }
                 }
             }
-            // stitch the four lists: my first run continues the previous lane's last run when both
-            // start from the same cell
-            const int prev_last = __shfl_up_sync(0xffffffffu, cur_id, 1, TM_T);
-            const int merge = (t > 0 && n > 0 && first_id == prev_last) ? 1 : 0;
-            const int mine = n - merge;
-            int incl = mine;
-            int up = __shfl_up_sync(0xffffffffu, incl, 1, TM_T);
-            if (t >= 1) incl += up;
-            up = __shfl_up_sync(0xffffffffu, incl, 2, TM_T);
-            if (t >= 2) incl += up;
-            nrun = __shfl_sync(0xffffffffu, incl, TM_T - 1, TM_T);
+            // stitch the four lists (one per warp) through shared memory: a lane's first run
+            // continues the previous quarter's last run when both start from the same cell
+            st_n[t * TM_PX + px] = n; st_first[t * TM_PX + px] = first_id; st_last[t * TM_PX + px] = cur_id;
+            __syncthreads();
+            int merge = 0, mine = 0, incl = 0;
+            nrun = 0;
+#pragma unroll
+            for (int u = 0; u < TM_T; ++u) {
+                const int nu = st_n[u * TM_PX + px];
+                const int mu = (u > 0 && nu > 0 && st_first[u * TM_PX + px] == st_last[(u > 0 ? u - 1 : 0) * TM_PX + px]) ? 1 : 0;
+                nrun += nu - mu;
+                if (u == t) { merge = mu; mine = nu - mu; incl = nrun; }
+            }
             my_run0 = incl - mine - merge;
             bool over = nrun > TM_MAXRUN;
             if (active && !over) {
@@ -440,8 +446,8 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
             // every lane evaluates an equal share of the planes -- its own quarter, the same planes
             // it walked in step 1 -- whichever lane accumulated their run.  (Evaluating "the planes
             // of my runs" instead leaves most lanes idle while one works through a 25-plane run.)
-            float* Gs = stage0;   // [run - first][10][PX], run stride padded by 8 floats (banks)
-            constexpr int GS_RUN = 10 * TM_PX + 8;
+            float* Gs = stage0;   // [run - first][10][PX]
+            constexpr int GS_RUN = 10 * TM_PX;
             static_assert(TM_T * NSLOT * GS_RUN <= TM_NSTAGE * TM_STAGE, "Gram exchange fits in the stages");
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j) {
@@ -497,15 +503,23 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
     // ---------------- 5. result tile -> global memory, one 128-byte row per warp-instruction ----
     __syncthreads();
     if (a.lsm != nullptr) {   // log_softmax over the planes (host guarantees PS == 1)
+        float* red = stage0;   // [T][PX] partials; the stages are idle
         float m = -INFINITY;
         for (int k = t; k < nk; k += TM_T) m = fmaxf(m, out_s[k * TM_OS + px]);
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        float s = 0.f;
-        for (int k = t; k < nk; k += TM_T) s += expf(out_s[k * TM_OS + px] - m);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (t == 0) { lsm_m[px] = m; lsm_l[px] = logf(s); }
+        red[t * TM_PX + px] = m;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < TM_T; ++u) m = fmaxf(m, red[u * TM_PX + px]);
+        float sum = 0.f;
+        for (int k = t; k < nk; k += TM_T) sum += expf(out_s[k * TM_OS + px] - m);
+        red[(TM_T + t) * TM_PX + px] = sum;
+        __syncthreads();
+        if (t == 0) {
+            sum = 0.f;
+#pragma unroll
+            for (int u = 0; u < TM_T; ++u) sum += red[(TM_T + u) * TM_PX + px];
+            lsm_m[px] = m; lsm_l[px] = logf(sum);
+        }
         __syncthreads();
     }
     {
