@@ -33,10 +33,10 @@
 namespace dpv {
 
 constexpr int TM_PX = 32, TM_T = 4, TM_NT = TM_PX * TM_T;
-constexpr int TM_WC = 52, TM_WR = 8;             // source window capacity (cols, rows)
+constexpr int TM_WC = 52, TM_WR = 6;             // source window capacity (cols, rows)
 constexpr int TM_CK = 8;                         // channels per stage
 constexpr int TM_NSTAGE = 2;
-constexpr int TM_MAXRUN = 32;                    // runs recorded per pixel and view
+constexpr int TM_MAXRUN = 24;                    // runs recorded per pixel and view
 constexpr int TM_ROW = TM_CK * TM_WC;            // floats of one window row (all channels of a chunk)
 constexpr int TM_WIN = TM_WR * TM_ROW;
 constexpr int TM_STAGE = TM_WIN + TM_CK * TM_PX; // + the reference pixels of the chunk
@@ -190,14 +190,14 @@ __device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* 
 }
 
 template <int NSLOT>
-__global__ void __launch_bounds__(TM_NT, 5)
+__global__ void __launch_bounds__(TM_NT, 6)
 sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map_src,
                       const __grid_constant__ CUtensorMap map_ref) {
     __shared__ __align__(128) float stage0[TM_NSTAGE * TM_STAGE];      // TMA destinations
     __shared__ int cell_s[TM_MAXRUN * TM_PX];                          // [MAXRUN][PX] cell of each run
     __shared__ short kst_s[(TM_MAXRUN + 1) * TM_PX];                   // [MAXRUN + 1][PX] first plane
     extern __shared__ __align__(16) float out_s[];                     // [kper][PX] result tile
-    __shared__ int st_n[TM_T * TM_PX], st_first[TM_T * TM_PX], st_last[TM_T * TM_PX];   // run-list stitching
+    __shared__ float geo_s[16];                                        // K R (9), K t (3), cx, cy of the view
     __shared__ unsigned long long full_bar[TM_NSTAGE];
     __shared__ TmShared ts;
     __shared__ float lsm_m[TM_PX], lsm_l[TM_PX];
@@ -235,23 +235,29 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
 
     for (int v = 0; v < a.V; ++v) {
         const float* src = a.src + (long long)b * a.src_bs + (long long)v * a.src_vs;
-        PixelTerm pt;
-        TmGeom g;
-        {
-            const ViewGeom vg = load_view_geom(a.K + (long long)b * a.k_bs,
-                                               a.pose + (long long)b * a.pose_bs + (long long)v * 16);
-            pt = pixel_term(vg, rx, ry, rz);
-            g.t1x = vg.t1[0]; g.t1y = vg.t1[1]; g.t1z = vg.t1[2]; g.cx = vg.cx; g.cy = vg.cy;
-            g.inv_cx = __frcp_rn(vg.cx); g.inv_cy = __frcp_rn(vg.cy);
-            g.half_w = (float)a.W * 0.5f; g.half_h = (float)a.H * 0.5f;
+        // ---------------- 0. view geometry: K R and K t once per CTA ---------------------------
+        if (tid < 12) {   // warping/homography.py:119-121; same dot3 order as load_view_geom
+            const float* Kp = a.K + (long long)b * a.k_bs + (tid < 9 ? tid / 3 : tid - 9) * 3;
+            const float* pp = a.pose + (long long)b * a.pose_bs + (long long)v * 16 + (tid < 9 ? tid % 3 : 3);
+            geo_s[tid] = dot3(__ldg(Kp), __ldg(Kp + 1), __ldg(Kp + 2), __ldg(pp), __ldg(pp + 4), __ldg(pp + 8));
+        } else if (tid < 14) {
+            geo_s[tid] = __ldg(a.K + (long long)b * a.k_bs + (tid == 12 ? 2 : 5));   // cx, cy
         }
-
-        // ---------------- 1. runs of this pixel: each lane walks its quarter of the planes ----
         if (tid == 0) {
             ts.bbox[0] = 1 << 30; ts.bbox[1] = -(1 << 30); ts.bbox[2] = 1 << 30; ts.bbox[3] = -(1 << 30);
             ts.max_runs = 0; ts.overflow = 0;
         }
-        __syncthreads();   // d_s, barrier init, ts; previous view done with cell_s / kst_s
+        __syncthreads();   // geo_s, d_s, barrier init, ts; previous view done with cell_s / kst_s
+        PixelTerm pt;
+        TmGeom g;
+        pt.x = dot3(geo_s[0], geo_s[1], geo_s[2], rx, ry, rz);
+        pt.y = dot3(geo_s[3], geo_s[4], geo_s[5], rx, ry, rz);
+        pt.z = dot3(geo_s[6], geo_s[7], geo_s[8], rx, ry, rz);
+        g.t1x = geo_s[9]; g.t1y = geo_s[10]; g.t1z = geo_s[11]; g.cx = geo_s[12]; g.cy = geo_s[13];
+        g.inv_cx = __frcp_rn(g.cx); g.inv_cy = __frcp_rn(g.cy);
+        g.half_w = (float)a.W * 0.5f; g.half_h = (float)a.H * 0.5f;
+
+        // ---------------- 1. runs of this pixel: each warp walks its quarter of the planes ----
         int nrun;          // runs of this pixel (all four lanes agree)
         int my_run0;       // run that holds my first plane
         {
@@ -285,6 +291,9 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
             }
             // stitch the four lists (one per warp) through shared memory: a lane's first run
             // continues the previous quarter's last run when both start from the same cell
+            int* st_n = (int*)stage0;                 // the stages are idle during run detection
+            int* st_first = st_n + TM_T * TM_PX;
+            int* st_last = st_first + TM_T * TM_PX;
             st_n[t * TM_PX + px] = n; st_first[t * TM_PX + px] = first_id; st_last[t * TM_PX + px] = cur_id;
             __syncthreads();
             int merge = 0, mine = 0, incl = 0;
