@@ -183,6 +183,9 @@ def run_ours(args, dpv):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout when NCCL_DEBUG is set in the environment;
+        # stdout carries exactly one JSON line, so send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

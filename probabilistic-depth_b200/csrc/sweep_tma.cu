@@ -112,7 +112,15 @@ struct TmGeom {
 // sweep_coord_fast with the reciprocal on the SFU (MUFU.RCP, ~1 ulp; the IEEE __frcp_rn expands
 // to ~10 instructions and was 6 % of the kernel).  Every phase uses this one function, so a plane
 // gets the same coordinate wherever it is recomputed.
+// EXACT: the reference's operation order with IEEE divisions (sweep_coord), for images wider than
+// ~200 px, where one ulp of a coordinate (6e-5 px at 1000 px) times a unit feature gradient is
+// already the size of the parity budget and the 2-3 ulp of the fast form would exceed it.
+template <bool EXACT>
 __device__ __forceinline__ void tm_coord(const TmGeom& g, const PixelTerm& p, float d, float& ix, float& iy) {
+    if (EXACT) {
+        sweep_coord(g.t1x, g.t1y, g.t1z, p, d, g.cx, g.cy, g.half_w, g.half_h, ix, iy);
+        return;
+    }
     const float px = fmaf(p.x, d, g.t1x);
     const float py = fmaf(p.y, d, g.t1y);
     const float pz = fmaf(p.z, d, g.t1z);
@@ -122,9 +130,10 @@ __device__ __forceinline__ void tm_coord(const TmGeom& g, const PixelTerm& p, fl
     ix = fmaf(fmaf(u - g.cx, g.inv_cx, 1.0f), g.half_w, -0.5f);
     iy = fmaf(fmaf(v - g.cy, g.inv_cy, 1.0f), g.half_h, -0.5f);
 }
+template <bool EXACT>
 __device__ __forceinline__ Tap tm_tap(const TmGeom& g, const PixelTerm& pt, float d) {
     float ix, iy;
-    tm_coord(g, pt, d, ix, iy);
+    tm_coord<EXACT>(g, pt, d, ix, iy);
     return make_tap(ix, iy);
 }
 
@@ -140,6 +149,7 @@ __device__ __forceinline__ float tm_quad(const float* G, float fx, float fy) {
 }
 
 // Window does not fit: planes [ka, kb) of one pixel with per-thread gathers from global memory.
+template <bool EXACT>
 __device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* __restrict__ src,
                                               const float* __restrict__ refp, const TmGeom& g,
                                               const PixelTerm& pt, const float* d_s, int ka, int kb,
@@ -148,7 +158,7 @@ __device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* 
     int k = ka;
     while (k < kb) {
         float ix, iy;
-        tm_coord(g, pt, d_s[k], ix, iy);
+        tm_coord<EXACT>(g, pt, d_s[k], ix, iy);
         const Tap tap = make_tap(ix, iy);
         const CellTaps cell = cell_taps(tap, H, W);
         float q[10];
@@ -174,7 +184,7 @@ __device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* 
             float* o = out_col + k * TM_OS;
             *o = first_view ? val : (*o + val);
             if (++k >= kb) break;
-            tm_coord(g, pt, d_s[k], ix, iy);
+            tm_coord<EXACT>(g, pt, d_s[k], ix, iy);
             const Tap nt = make_tap(ix, iy);
             if (outside) {
                 if (cell_taps(nt, H, W).id >= 0) break;
@@ -189,7 +199,7 @@ __device__ __noinline__ void tm_gather_planes(int C, int H, int W, const float* 
     }
 }
 
-template <int NSLOT>
+template <int NSLOT, bool EXACT>
 __global__ void __launch_bounds__(TM_NT, 6)
 sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map_src,
                       const __grid_constant__ CUtensorMap map_ref) {
@@ -267,7 +277,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
             if (active) {
                 for (int k = wa; k < wb; ++k) {
                     float ix, iy;
-                    tm_coord(g, pt, d_s[k], ix, iy);
+                    tm_coord<EXACT>(g, pt, d_s[k], ix, iy);
                     const Tap tap = make_tap(ix, iy);
                     const bool inside = (tap.x0 >= -1) & (tap.x0 < a.W) & (tap.y0 >= -1) & (tap.y0 < a.H);
                     const int id = inside ? tm_pack(tap.x0, tap.y0) : kTmOutside;
@@ -315,7 +325,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                     m &= m - 1;
                     if (gi >= incl - mine) {       // not the merged one
                         const int k = wa + i;
-                        const Tap tap = tm_tap(g, pt, d_s[k]);
+                        const Tap tap = tm_tap<EXACT>(g, pt, d_s[k]);
                         const bool inside = (tap.x0 >= -1) & (tap.x0 < a.W) & (tap.y0 >= -1) & (tap.y0 < a.H);
                         cell_s[gi * TM_PX + px] = inside ? tm_pack(tap.x0, tap.y0) : kTmOutside;
                         kst_s[gi * TM_PX + px] = (short)k;
@@ -348,7 +358,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
 
         if (!fits) {
             if (active && wa < wb)
-                tm_gather_planes(a.C, a.H, a.W, src, ref + p, g, pt, d_s, wa, wb, inv_sigma, out_s + px, v == 0);
+                tm_gather_planes<EXACT>(a.C, a.H, a.W, src, ref + p, g, pt, d_s, wa, wb, inv_sigma, out_s + px, v == 0);
             continue;   // next view (uniform across the CTA)
         }
 
@@ -471,7 +481,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                 }
             }
             __syncthreads();
-            if (active) {
+            if (active && first < nrun) {   // (a pixel with fewer runs has nothing in this pass)
                 const int last = min(first + TM_T * NSLOT, nrun);   // runs [first, last) are in Gs
                 int k = max(wa, (int)kst_s[first * TM_PX + px]);
                 const int kend = min(wb, (int)kst_s[last * TM_PX + px]);
@@ -497,7 +507,7 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                     float val = rr;
                     if (!outside) {
                         float ix, iy;
-                        tm_coord(g, pt, d_s[k], ix, iy);
+                        tm_coord<EXACT>(g, pt, d_s[k], ix, iy);
                         val = tm_quad(gq, ix - fx0, iy - fy0);
                     }
                     val *= inv_sigma;
@@ -582,7 +592,7 @@ bool sweep_gram_tma_supported(const SweepArgs& a) {
 }
 
 int launch_sweep_gram_tma(const SweepArgs& a, cudaStream_t st) {
-    static const int nslot = [] { const char* e = getenv("DPV_SWEEP_TMA_NSLOT"); return e ? atoi(e) : 0; }();
+    static const int exact_env = [] { const char* e = getenv("DPV_SWEEP_TMA_EXACT"); return e ? atoi(e) : -1; }();
     if (!sweep_gram_tma_supported(a)) return DPV_E_UNSUPP;
     tm_encode_fn enc = tm_encoder();
     const int kper = (a.D + a.PS - 1) / a.PS;
@@ -614,15 +624,17 @@ int launch_sweep_gram_tma(const SweepArgs& a, cudaStream_t st) {
     const size_t smem = tm_smem_bytes(kper);
     const int tiles = ((a.W + TM_PX - 1) / TM_PX) * a.H;
     dim3 grid(tiles, a.PS, a.B), block(TM_NT);
+    // coordinates: reference operation order for wide images (see tm_coord), SFU form otherwise
+    const bool exact = exact_env >= 0 ? (exact_env != 0) : (a.W > 192 || a.H > 192);
     cudaError_t e;
-    if (nslot == 2) {
-        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (exact) {
+        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        sweep_gram_tma_kernel<2><<<grid, block, smem, st>>>(a, msrc, mref);
+        sweep_gram_tma_kernel<4, true><<<grid, block, smem, st>>>(a, msrc, mref);
     } else {
-        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(sweep_gram_tma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        sweep_gram_tma_kernel<4><<<grid, block, smem, st>>>(a, msrc, mref);
+        sweep_gram_tma_kernel<4, false><<<grid, block, smem, st>>>(a, msrc, mref);
     }
     DPV_LAUNCH_END();
     return 0;

@@ -106,8 +106,9 @@ class FrameStep:
                                   B, D, H, W, 9, ops.IN_LOGPROB, *self.uf_params, self.pad_depth, st))
 
     def launches_per_step(self):
-        n = {"default": 5, "upsample": 6, "feedback": 7}[self.mode]
-        return n - 1 if self.fused_uf else n     # head + UF partial/finish: 3 launches -> 2
+        # sweep, 1/4-res soft-max, head, UF (weights + partial sums + finish); fused: stream kernel + finish
+        n = {"default": 6, "upsample": 7, "feedback": 8}[self.mode]
+        return n - 2 if self.fused_uf else n
 
     # -- algorithmic bytes, per step ---------------------------------
     def algorithmic_bytes(self):
