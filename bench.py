@@ -173,6 +173,14 @@ def run_reference(args, dpv):
     print(json.dumps(line), flush=True)
 
 
+def alg_of(name, alg):
+    """Algorithmic bytes of the launch(es) timed under `name` (FrameStep.algorithmic_bytes keys)."""
+    return {"sweep": alg.get("sweep", 0), "head_quarter": alg.get("head_quarter", 0),
+            "head_full": alg.get("head_full", 0), "ufield": alg.get("ufield", 0),
+            "head_full_ufield": alg.get("head_full", 0), "bayes_fuse": alg.get("bayes_fuse", 0),
+            "warp_feature": alg.get("warp_feature", 0), "feedback_fuse": alg.get("feedback_fuse", 0)}.get(name, 0)
+
+
 def run_ours(args, dpv):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -198,7 +206,8 @@ def run_ours(args, dpv):
     B = WL["B"]
     hi = host_inputs(dpv, B, seed=rank)
     step = frame_mod.FrameStep(B, WL["V"], WL["C"], WL["D"], WL["h"], WL["w"], WL["H"], WL["W"], hi["d"],
-                               sigma=10.0, mode="default", device=dev, fuse_uf=args.fuse_uf)
+                               sigma=10.0, mode="default", device=dev, fuse_uf=args.fuse_uf,
+                               fuse_lsm=not args.no_fuse_lsm)
     # two input sets in HBM, alternated: 2 x 227 MB read + 227 MB written per step >> 126 MB L2
     nset = 2
     dsets = []
@@ -234,6 +243,22 @@ def run_ours(args, dpv):
     launches = dpv._lib.launch_count() - l0
     ms = t_start.elapsed_time(t_end)
     head_ms = [a.elapsed_time(b) for a, b in ev]
+
+    # ---- per-kernel breakdown (separate short loop: events between every launch) -----------
+    kev = {}
+    kcur = {"i": 0}
+    nbk = 20
+
+    def khook(name, which):
+        lst = kev.setdefault(name, [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(nbk)])
+        lst[kcur["i"]][which].record()
+
+    for i in range(nbk):
+        s_ = dsets[i % nset]
+        kcur["i"] = i
+        step.run(s_["feats"], s_["poses"], s_["K"], s_["rays"], s_["logits"], s_["intr_up"], kernel_hook=khook)
+    torch.cuda.synchronize()
+    kernel_ms = {n: statistics.median(a.elapsed_time(b) for a, b in lst) for n, lst in kev.items()}
 
     # ---- end to end through the host-buffer pipeline --------------------------------------
     pipe = pipe_mod.FramePipeline(B, WL["V"], WL["C"], WL["D"], WL["h"], WL["w"], WL["H"], WL["W"],
@@ -285,6 +310,7 @@ def run_ours(args, dpv):
                        "kernels_per_step": step.launches_per_step(),
                        "algorithmic_bytes_per_step": alg,
                        "uf_fused_into_head": bool(step.fused_uf),
+                       "quarter_log_softmax_in_sweep_epilogue": bool(step.fuse_lsm),
                        "frame_hbm_frac": sum(alg.values()) / (ms / args.steps * 1e-3) / 1e9 / peak,
                        "frame_hbm_frac_note": "SURVEY 8d bytes/frame (K5 counted as its own pass) / time / peak"},
             "roofline": {"kernel": head_name, "bound": "hbm",
@@ -297,6 +323,19 @@ def run_ours(args, dpv):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        # where the step goes (rank 0, events around every launch, separate 20-step loop) and the
+        # sweep kernel against the roof that binds it: it moves 6 % of the bytes but is FP32-bound
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # SMs x lanes x 2 x max clock (derived)
+        sw_ms = kernel_ms.get("sweep")
+        line["kernels"] = {
+            n: {"ms": ms_k, "algorithmic_GBs": (alg_of(n, alg) / (ms_k * 1e-3) / 1e9) if alg_of(n, alg) else None}
+            for n, ms_k in kernel_ms.items()}
+        if sw_ms:
+            line["sweep"] = {"bound": "fp32", "direct_form_flops_per_launch": step.sweep_flops(),
+                             "achieved_TFLOPs_direct_form": step.sweep_flops() / (sw_ms * 1e-3) / 1e12,
+                             "fp32_peak_TFLOPs": fp32_peak, "peak_kind": "derived",
+                             "note": "flops of the direct (per-plane, 4-tap) form; the Gram form executes ~2.3x fewer",
+                             "includes_quarter_log_softmax": bool(step.fuse_lsm)}
         if world == 1 and not args.no_cpu_baseline:
             import warnings
             warnings.filterwarnings("ignore")
@@ -318,6 +357,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fuse-uf", action="store_true",
                     help="run K3+K5 as the single fused TMA-fed kernel instead of dpv_head + dpv_ufield")
+    ap.add_argument("--no-fuse-lsm", action="store_true",
+                    help="1/4-res log-softmax as its own dpv_head launch instead of the sweep kernel's epilogue")
     args = ap.parse_args()
     dpv = importlib.import_module("probabilistic-depth_b200")
     if args.impl == "reference":

@@ -19,7 +19,7 @@ from . import _lib, ops
 
 class FrameStep:
     def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None,
-                 fuse_uf=False):
+                 fuse_uf=False, fuse_lsm=True):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dev = dev
         self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W = B, V, C, D, h, w, H, W
@@ -38,6 +38,12 @@ class FrameStep:
         self.uf = e(B, D, W)
         self.dz = e(B, H, W)
         self.lib = _lib.load()
+        # 1/4-res log-softmax as an epilogue of the sweep kernel (the cost tile is still in shared
+        # memory; models/packnet.py:394 places them back to back) instead of a dpv_head launch.  The
+        # TMA-fed kernel that has this epilogue needs 16-byte row strides.
+        # The epilogue needs all planes of a pixel in one CTA, i.e. no plane split: only when the batch
+        # alone fills the machine (the launcher splits planes below 148 x 8 warps of pixels).
+        self.fuse_lsm = bool(fuse_lsm) and (w % 4 == 0) and B * h * ((w + 31) // 32) >= 148 * 8
         # K3 + K5 either as dpv_head followed by dpv_ufield (default: the short-CTA head kernel runs at
         # ~85 % of the HBM roof and the UF pass re-reads only the road-band tiles) or in one pass with
         # the persistent TMA-fed kernel (fuse_uf=True; same step time at 8 x 256 x 384, see
@@ -59,7 +65,7 @@ class FrameStep:
 
     # -- one batch of frames ---------------------------------------------------------------
     def run(self, feats, poses, K, rays, logits_full, intr_up, dmaps=None, masks=None,
-            feat_raw=None, bv_resi=None, head_hook=None):
+            feat_raw=None, bv_resi=None, head_hook=None, kernel_hook=None):
         """feats [B,V+1,C,h,w] (reference view last); poses [B,V+1,4,4]; K [B,3,3]; rays
         [B,3,h*w]; logits_full [B,D,H,W] (the decoder's pre-softmax output); intr_up [B,3,3].
         upsample: dmaps [B,h,w], masks [B,1,h,w].  feedback: feat_raw [B,V+1,D,h,w], bv_resi
@@ -67,47 +73,71 @@ class FrameStep:
         B, V, C, D, h, w, H, W = self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W
         lib, st = self.lib, torch.cuda.current_stream().cuda_stream
         p = lambda t: None if t is None else t.data_ptr()
+        hk = kernel_hook if kernel_hook is not None else (lambda name, which: None)
         chw = C * h * w
         fp = feats.data_ptr()
+        hk("sweep", 0)
         _lib.check(lib.dpv_sweep_cost_volume(
-            fp + 4 * V * chw, fp, p(poses), p(K), p(rays), p(self.d), p(self.cost), None,
+            fp + 4 * V * chw, fp, p(poses), p(K), p(rays), p(self.d), p(self.cost),
+            p(self.bv) if self.fuse_lsm else None,
             B, V, C, D, h, w, (V + 1) * chw, (V + 1) * chw, chw, (V + 1) * 16, 9, 3 * h * w,
             self.sigma, 0, 0, st))
-        _lib.check(lib.dpv_head(p(self.cost), None, p(self.d), p(self.bv), None, None, None, None,
-                                None, B, D, h, w, ops.IN_LOGITS, st))
+        hk("sweep", 1)
+        if not self.fuse_lsm:
+            hk("head_quarter", 0)
+            _lib.check(lib.dpv_head(p(self.cost), None, p(self.d), p(self.bv), None, None, None, None,
+                                    None, B, D, h, w, ops.IN_LOGITS, st))
+            hk("head_quarter", 1)
         if self.mode == "upsample":
+            hk("bayes_fuse", 0)
             _lib.check(lib.dpv_bayes_fuse(p(self.bv), None, p(dmaps), p(masks), p(self.d),
                                           p(self.fused), p(self.logfused), B, D, h, w, self.two_sig, st))
+            hk("bayes_fuse", 1)
         elif self.mode == "feedback":
+            hk("warp_feature", 0)
             _lib.check(lib.dpv_warp_feature(p(feat_raw), p(poses), p(K), p(rays), p(self.d),
                                             p(self.warped), B, V + 1, D, h, w, (V + 1) * 16, 9,
                                             3 * h * w, st))
+            hk("warp_feature", 1)
+            hk("feedback_fuse", 0)
             _lib.check(lib.dpv_head(p(self.bv), p(bv_resi), p(self.d), p(self.bv_upd), None, None,
                                     None, None, None, B, D, h, w, ops.IN_LOGITS, st))
+            hk("feedback_fuse", 1)
+        self._full_res(lib, st, p, logits_full, intr_up, head_hook, hk)
+
+    def _full_res(self, lib, st, p, logits_full, intr_up, head_hook, hk):
+        B, D, H, W = self.B, self.D, self.H, self.W
         if head_hook is not None:
             head_hook(0)
+        hk("head_full_ufield" if self.fused_uf else "head_full", 0)
         if self.fused_uf:
             _lib.check(lib.dpv_head_ufield(p(logits_full), p(self.d), p(self.refined), p(self.depth),
                                            p(self.var), p(self.argmax), p(self.quarter), p(intr_up),
                                            p(self.tabs[0]), p(self.tabs[1]), p(self.uf), p(self.dz),
                                            p(self.ws), B, D, H, W, 9, ops.IN_LOGITS, *self.uf_params,
                                            self.pad_depth, st))
+            hk("head_full_ufield", 1)
             if head_hook is not None:
                 head_hook(1)
             return
         _lib.check(lib.dpv_head(p(logits_full), None, p(self.d), p(self.refined), None, p(self.depth),
                                 p(self.var), p(self.argmax), p(self.quarter), B, D, H, W,
                                 ops.IN_LOGITS, st))
+        hk("head_full", 1)
         if head_hook is not None:
             head_hook(1)
         rf, ri, cf, ci = self.luts
+        hk("ufield", 0)
         _lib.check(lib.dpv_ufield(p(self.refined), p(self.depth), p(self.d), p(intr_up), None,
                                   p(rf), p(ri), p(cf), p(ci), p(self.uf), p(self.dz), p(self.ws),
                                   B, D, H, W, 9, ops.IN_LOGPROB, *self.uf_params, self.pad_depth, st))
+        hk("ufield", 1)
 
     def launches_per_step(self):
         # sweep, 1/4-res soft-max, head, UF (weights + partial sums + finish); fused: stream kernel + finish
         n = {"default": 6, "upsample": 7, "feedback": 8}[self.mode]
+        if self.fuse_lsm:
+            n -= 1
         return n - 2 if self.fused_uf else n
 
     # -- algorithmic bytes, per step ---------------------------------
@@ -126,6 +156,10 @@ class FrameStep:
             k["warp_feature"] = 8 * hw * D * (V + 1) + 12 * hw
             k["feedback_fuse"] = 12 * hw * D
         return {n: v * B for n, v in k.items()}
+
+    def sweep_flops(self):
+        """Direct-form flops of K1+K2a per step: hw * D * V * (11 C + 40) per frame."""
+        return self.B * self.h * self.w * self.D * self.V * (11 * self.C + 40)
 
     def dominant_kernel(self):
         """(name, algorithmic bytes per launch) of the kernel the roofline is quoted on: the
