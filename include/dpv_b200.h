@@ -198,6 +198,25 @@ int dpv_shard_finish(const float* x, const float* global_max, const float* globa
 int dpv_shard_argmax_merge(const float* vals, const float* idx, int64_t* out, int G, int64_t n,
                            void* stream);
 
+/* ---- eval metrics on the device ------------------------------------
+ * dpv_depth_errors replaces img_utils.depth_error (utils/img_utils.py:17-22) around depthError
+ * (external/deval_lib/src/evaluate_depth.h:19-119), batched: first/second [B,H,W] in the python
+ * wrapper's argument order (prediction first; pixels with first >= 0 count).  zero_invalid != 0 maps
+ * zeros to -1 as the wrapper does.  Optional fused preparation of trainer/default_trainer.py:247-254:
+ * mask [B,H,W] multiplies `first`; clamp_max > 0 clamps `second` from above.  out [B,9] in the order
+ * mae, rmse, inverse mae, inverse rmse, log mae, log rmse, scale invariant log, abs relative,
+ * squared relative; counts [B] (optional) = valid pixels (0 => the reference throws; out is NaN).
+ * workspace: dpv_depth_errors_workspace_doubles(B, H, W) doubles.
+ * dpv_unc_rmse replaces compute_unc_rmse (utils/img_utils.py:183-194): uf_* [B,D,W] linear
+ * uncertainty fields -> out [B] mean |E_truth - E_pred| over the columns where both are finite.
+ */
+int64_t dpv_depth_errors_workspace_doubles(int B, int H, int W);
+int dpv_depth_errors(const float* first, const float* second, const float* mask, float clamp_max,
+                     int zero_invalid, float* out, int* counts, double* workspace,
+                     int B, int H, int W, void* stream);
+int dpv_unc_rmse(const float* uf_truth, const float* uf_pred, const float* d_candi, float* out,
+                 int B, int D, int W, void* stream);
+
 /* ---- whole-frame host pipeline (end-to-end with HOST buffers) ---------------------------
  * What a non-PyTorch host (the reference's ROS node, ros/ros_net.py:241-303) would call: one
  * object owning device staging buffers, streams and events; run() takes pinned or pageable

@@ -37,5 +37,6 @@ def patch_reference(homography=None, img_utils=None):
         for n in ("est_swp_volume_v4", "warp_feature", "_back_warp_homo_parallel"):
             setattr(homography, n, getattr(ours_h, n))
     if img_utils is not None:
-        for n in ("dpv_to_depthmap", "gen_dpv_withmask", "gen_ufield", "compute_unc_field"):
+        for n in ("dpv_to_depthmap", "gen_dpv_withmask", "gen_ufield", "compute_unc_field",
+                  "depth_error", "eval_errors", "compute_unc_rmse"):
             setattr(img_utils, n, getattr(ours_u, n))

@@ -37,6 +37,9 @@ PROTOTYPES = {
     "dpv_shard_central": (_c_i, [_c_fp] * 5 + [_c_i] * 3 + [_c_fp]),
     "dpv_shard_finish": (_c_i, [_c_fp] * 7 + [_c_i] * 3 + [_c_fp]),
     "dpv_shard_argmax_merge": (_c_i, [_c_fp] * 3 + [_c_i, _c_i64, _c_fp]),
+    "dpv_depth_errors_workspace_doubles": (_c_i64, [_c_i] * 3),
+    "dpv_depth_errors": (_c_i, [_c_fp] * 3 + [_c_f, _c_i] + [_c_fp] * 3 + [_c_i] * 3 + [_c_fp]),
+    "dpv_unc_rmse": (_c_i, [_c_fp] * 4 + [_c_i] * 3 + [_c_fp]),
     "dpv_pipeline_create": (_c_i, [ctypes.POINTER(ctypes.c_void_p)] + [_c_i] * 9),
     "dpv_pipeline_destroy": (_c_i, [ctypes.c_void_p]),
     "dpv_pipeline_run": (_c_i, [ctypes.c_void_p] + [_c_fp] * 11 + [_c_f] + [_c_fp] * 7),

@@ -425,3 +425,50 @@ def correlation(x1, x2, max_displacement=4):
     _lib.check(_lib.load().dpv_correlation(_p(x1), _p(x2), _p(out), B, C, H, W,
                                            int(max_displacement), _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- eval metrics
+METRIC_NAMES = ["mae", "rmse", "inverse mae", "inverse rmse", "log mae", "log rmse",
+                "scale invariant log", "abs relative", "squared relative"]
+
+
+def depth_errors(predicted, truth, mask=None, clamp_max=None, zero_invalid=True, want_counts=False):
+    """The nine KITTI depth metrics per item, on the device (reference utils/img_utils.py:17-22 around
+    external/deval_lib/src/evaluate_depth.h:19-119).  predicted, truth [B,H,W] (or [H,W]); optional
+    fused preparation of trainer/default_trainer.py:247-254: `mask` multiplies the prediction,
+    `clamp_max` clamps the truth from above.  Returns [B,9] (METRIC_NAMES order) and, on request, the
+    number of valid pixels per item."""
+    _need(predicted, "predicted"), _need(truth, "truth")
+    if predicted.dim() == 2:
+        predicted, truth = predicted.unsqueeze(0), truth.unsqueeze(0)
+        mask = None if mask is None else mask.reshape(1, *mask.shape[-2:])
+    if predicted.shape != truth.shape or predicted.dim() != 3:
+        raise ValueError("predicted and truth must both be [B,H,W]")
+    predicted, truth = predicted.contiguous(), truth.contiguous()
+    B, H, W = predicted.shape
+    if mask is not None:
+        mask = _need(mask, "mask").reshape(B, H, W).contiguous()
+    lib = _lib.load()
+    out = torch.empty((B, 9), device=predicted.device, dtype=torch.float32)
+    counts = torch.empty((B,), device=predicted.device, dtype=torch.int32)
+    ws = torch.empty((int(lib.dpv_depth_errors_workspace_doubles(B, H, W)),), device=predicted.device,
+                     dtype=torch.float64)
+    _lib.check(lib.dpv_depth_errors(_p(predicted), _p(truth), _p(mask),
+                                    float(clamp_max) if clamp_max is not None else 0.0,
+                                    1 if zero_invalid else 0, _p(out), _p(counts), _p(ws), B, H, W, _stream()))
+    return (out, counts) if want_counts else out
+
+
+def unc_rmse(uf_truth, uf_pred, d_candi):
+    """compute_unc_rmse (reference utils/img_utils.py:183-194), batched: uf_* [B,D,W] -> [B]."""
+    _need(uf_truth, "uf_truth"), _need(uf_pred, "uf_pred")
+    if uf_truth.shape != uf_pred.shape or uf_truth.dim() != 3:
+        raise ValueError("uncertainty fields must both be [B,D,W]")
+    uf_truth, uf_pred = uf_truth.contiguous(), uf_pred.contiguous()
+    B, D, W = uf_truth.shape
+    d = depth_bins(d_candi, uf_truth.device)
+    if d.numel() != D:
+        raise ValueError("d_candi has %d bins, the fields %d" % (d.numel(), D))
+    out = torch.empty((B,), device=uf_truth.device, dtype=torch.float32)
+    _lib.check(_lib.load().dpv_unc_rmse(_p(uf_truth), _p(uf_pred), _p(d), _p(out), B, D, W, _stream()))
+    return out

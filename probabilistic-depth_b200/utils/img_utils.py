@@ -1,7 +1,8 @@
 """Drop-in for the DPV helpers of the reference's utils/img_utils.py.
 
-Mirrors dpv_to_depthmap (:52-61), powerf (:80-85), compute_unc_field (:178-181),
-gen_ufield (:268-358) and gen_dpv_withmask (:360-375) of
+Mirrors eval_errors (:14-15), depth_error (:17-22), dpv_to_depthmap (:52-61), powerf (:80-85),
+compute_unc_field (:178-181), compute_unc_rmse (:183-202), gen_ufield (:268-358) and
+gen_dpv_withmask (:360-375) of
 /root/reference/utils/img_utils.py with the same names, arguments and error
 behaviour; the arithmetic runs in libdpv_sm100a.so.
 """
@@ -69,3 +70,51 @@ def compute_unc_field(dpv_refined_predicted, dpv_refined_truth, d_candi, intr_re
     unc_field_predicted, debugmap = gen_ufield(dpv_refined_predicted, d_candi,
                                                intr_refined.squeeze(0), BV_log=True, cfg=cfg)
     return unc_field_truth, unc_field_predicted, debugmap
+
+
+# ---------------------------------------------------------------- eval metrics
+def _as_cuda(a):
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            raise RuntimeError("depth_error: tensors must live on a CUDA device (no CPU path)")
+        return a.float()
+    # the reference passes .cpu().numpy() arrays (trainer/default_trainer.py:255-256); take them back
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def depth_error(predicted, truth):
+    """utils/img_utils.py:17-22.  [H,W] arrays or CUDA tensors -> list of the nine metrics, as the
+    reference's pybind call returns it.  (ops.depth_errors keeps a whole batch on the device.)"""
+    out, counts = ops.depth_errors(_as_cuda(predicted), _as_cuda(truth), want_counts=True)
+    if int(counts[0]) == 0:
+        # evaluate_depth.h:92-95 prints this and throws
+        raise RuntimeError("ERROR: Ground truth defect => Please write me an email!")
+    return [float(v) for v in out[0].cpu()]
+
+
+def eval_errors(errors):
+    """utils/img_utils.py:14-15 -> evaluateErrors (external/deval_lib/src/evaluate_depth.h:121-142):
+    {metric: [mean, min, max]} over the per-item vectors.  Host-side bookkeeping in the reference too
+    (a std::vector of 9-vectors); kept in float32 with utils.h's accumulators -- the sum runs in item
+    order, the minimum starts at 1 and the maximum at 0 (utils.h:24-56)."""
+    errs = np.asarray(errors, dtype=np.float32).reshape(-1, 9)
+    out = {}
+    for j, name in enumerate(ops.METRIC_NAMES):
+        col = errs[:, j]
+        mean = np.cumsum(col, dtype=np.float32)[-1] / np.float32(len(col))
+        mn = np.float32(1)
+        mx = np.float32(0)
+        for v in col:
+            if v < mn:
+                mn = v
+            if v > mx:
+                mx = v
+        out[name] = [float(mean), float(mn), float(mx)]
+    return out
+
+
+def compute_unc_rmse(unc_field_truth, unc_field_predicted, d_candi, plot=False):
+    """utils/img_utils.py:183-202 (the plot branch needs matplotlib and is visualisation only)."""
+    if plot:
+        raise NotImplementedError("compute_unc_rmse: plot=True is visualisation only")
+    return ops.unc_rmse(unc_field_truth, unc_field_predicted, d_candi)[0]

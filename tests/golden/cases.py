@@ -145,3 +145,49 @@ def corr_case(name):
 
 
 CORR_CASES = ["tiny", "lvl", "c96"]
+
+
+# ------------------------------------------------------------------ eval metrics
+def metrics_case(name):
+    """(predicted, truth) depth maps as trainer/default_trainer.py:246-256 hands them to depth_error:
+    truth sparse (LiDAR-like, zeros = no return), prediction dense times the truth's mask."""
+    spec = {
+        # name:        (H,   W,   keep, noise, seed)
+        "small":       (16,  24,  0.5,  1.0,   41),
+        "quarter":     (64,  96,  0.3,  1.5,   42),
+        "full":        (256, 384, 0.2,  2.0,   43),
+        "dense":       (37,  51,  1.0,  0.5,   44),
+        "one_pixel":   (8,   8,   0.0,  1.0,   45),
+    }[name]
+    H, W, keep, noise, seed = spec
+    r = synth.rng(seed)
+    truth = r.uniform(5.0, 45.0, (H, W)).astype(np.float32)
+    m = (r.uniform(0, 1, (H, W)) < keep)
+    if name == "one_pixel":
+        m[3, 5] = True
+    truth = (truth * m).astype(np.float32)
+    pred = np.clip(truth + noise * r.standard_normal((H, W)).astype(np.float32), 0.5, 60.0).astype(np.float32)
+    pred = (pred * m).astype(np.float32)
+    return dict(predicted=pred, truth=truth, mask=m.astype(np.float32), d_max=40.0)
+
+
+METRICS_CASES = ["small", "quarter", "full", "dense", "one_pixel"]
+
+
+def unc_rmse_case(name):
+    """Two linear uncertainty fields [1, D, W] with NaN columns, as compute_unc_field produces them."""
+    D, W, seed = {"small": (16, 24, 51), "full": (64, 384, 52)}[name]
+    r = synth.rng(seed)
+    d = synth.depth_candidates(5.0, 40.0, D, 1.0)
+
+    def field(shift):
+        x = r.standard_normal((1, D, W)).astype(np.float32) * 2 + shift
+        e = np.exp(x - x.max(1, keepdims=True))
+        f = (e / e.sum(1, keepdims=True)).astype(np.float32)
+        nan_cols = r.uniform(0, 1, W) < 0.2
+        f[:, :, nan_cols] = np.nan
+        return f
+    return dict(truth=field(0.0), pred=field(0.3), d_candi=d)
+
+
+UNC_RMSE_CASES = ["small", "full"]
