@@ -82,6 +82,17 @@ def main():
     poses = cu(s.stereo_poses(B) if args.pose == "stereo" else s.mono_poses(B))
     res = {}
 
+    # bring the clocks up before the first measurement (an idle B200 sits at 120 MHz and takes a few
+    # hundred ms of load to reach its boost clock: the first section measured would otherwise look slow)
+    _w = torch.empty((64, 1024, 1024), device="cuda")
+    _t0 = torch.cuda.Event(enable_timing=True); _t1 = torch.cuda.Event(enable_timing=True)
+    _t0.record()
+    for _ in range(300):
+        _w.mul_(1.0001)
+    _t1.record()
+    torch.cuda.synchronize()
+    del _w
+
     def want(n):
         return not args.only or n in args.only.split(",")
 
