@@ -217,6 +217,26 @@ int dpv_depth_errors(const float* first, const float* second, const float* mask,
 int dpv_unc_rmse(const float* uf_truth, const float* uf_pred, const float* d_candi, float* out,
                  int B, int D, int W, void* stream);
 
+/* ---- LiDAR -> sparse depth maps -----------------------------------
+ * dpv_lidar_depthmap replaces generate_depth (external/utils_lib/python/utils_lib.cpp:86-160, the
+ * upsample = 0 branch that kittiloader/kitti.py:693-697 uses for evaluation) followed by
+ * minpool(., pool_scale, pool_default) (utils/img_utils.py:87-95 via kittiloader/kitti.py:706):
+ * velo [n,4] (x, y, z, 1; 16-byte aligned), intr [3,4], m_velo2cam [4,4] row-major ->
+ *   dmap       [height, width]                         filtered z-buffer (0 = no return)       optional
+ *   dmap_small [height/pool_scale, width/pool_scale]   minimum of the non-zero depths per block optional
+ *   mask_small same shape: 1 where dmap_small >= 0.01 (kittiloader/kitti.py:713-714 builds the
+ *              complement), the `masks` input of dpv_bayes_fuse                               optional
+ * zbuf: width*height uint32 scratch.  filtering = neighbourhood half-width, filterdiff = tolerated
+ * depth step (utils_lib.cpp:89-92).
+ * dpv_minpool is the stand-alone minpool over N planes (default_value 0 = plain minimum).
+ */
+int dpv_lidar_depthmap(const float* velo, int n, const float* intr, const float* m_velo2cam,
+                       int width, int height, int filtering, float filterdiff, int pool_scale,
+                       float pool_default, unsigned* zbuf, float* dmap, float* dmap_small,
+                       float* mask_small, void* stream);
+int dpv_minpool(const float* in, float* out, int N, int H, int W, int scale, float default_value,
+                void* stream);
+
 /* ---- whole-frame host pipeline (end-to-end with HOST buffers) ---------------------------
  * What a non-PyTorch host (the reference's ROS node, ros/ros_net.py:241-303) would call: one
  * object owning device staging buffers, streams and events; run() takes pinned or pageable

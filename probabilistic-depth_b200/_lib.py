@@ -40,6 +40,8 @@ PROTOTYPES = {
     "dpv_depth_errors_workspace_doubles": (_c_i64, [_c_i] * 3),
     "dpv_depth_errors": (_c_i, [_c_fp] * 3 + [_c_f, _c_i] + [_c_fp] * 3 + [_c_i] * 3 + [_c_fp]),
     "dpv_unc_rmse": (_c_i, [_c_fp] * 4 + [_c_i] * 3 + [_c_fp]),
+    "dpv_lidar_depthmap": (_c_i, [_c_fp, _c_i, _c_fp, _c_fp] + [_c_i] * 3 + [_c_f, _c_i, _c_f] + [_c_fp] * 5),
+    "dpv_minpool": (_c_i, [_c_fp, _c_fp] + [_c_i] * 4 + [_c_f, _c_fp]),
     "dpv_pipeline_create": (_c_i, [ctypes.POINTER(ctypes.c_void_p)] + [_c_i] * 9),
     "dpv_pipeline_destroy": (_c_i, [ctypes.c_void_p]),
     "dpv_pipeline_run": (_c_i, [ctypes.c_void_p] + [_c_fp] * 11 + [_c_f] + [_c_fp] * 7),

@@ -472,3 +472,38 @@ def unc_rmse(uf_truth, uf_pred, d_candi):
     out = torch.empty((B,), device=uf_truth.device, dtype=torch.float32)
     _lib.check(_lib.load().dpv_unc_rmse(_p(uf_truth), _p(uf_pred), _p(d), _p(out), B, D, W, _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- LiDAR depth maps
+def lidar_depthmap(velo, intr, m_velo2cam, width, height, filtering=2, filterdiff=1.0, pool_scale=4,
+                   pool_default=1000.0, want_large=True, want_small=True, want_mask=True):
+    """generate_depth (reference external/utils_lib/python/utils_lib.cpp:86-160, upsample = 0) followed
+    by minpool (utils/img_utils.py:87-95 via kittiloader/kitti.py:706).  velo [n,4] (x, y, z, 1), intr
+    [3,4], m_velo2cam [4,4] on the device.  Returns (dmap [height,width], dmap_small, mask_small), None
+    for the ones not requested."""
+    _need(velo, "velo"), _need(intr, "intr"), _need(m_velo2cam, "m_velo2cam")
+    if velo.dim() != 2 or velo.shape[1] != 4 or intr.shape != (3, 4) or m_velo2cam.shape != (4, 4):
+        raise ValueError("velo [n,4], intr [3,4], m_velo2cam [4,4] expected")
+    velo, intr, m_velo2cam = velo.contiguous(), intr.contiguous(), m_velo2cam.contiguous()
+    dev = velo.device
+    zbuf = torch.empty((height, width), device=dev, dtype=torch.int32)
+    h2, w2 = height // pool_scale, width // pool_scale
+    dmap = torch.empty((height, width), device=dev, dtype=torch.float32) if want_large else None
+    small = torch.empty((h2, w2), device=dev, dtype=torch.float32) if want_small else None
+    mask = torch.empty((h2, w2), device=dev, dtype=torch.float32) if want_mask else None
+    _lib.check(_lib.load().dpv_lidar_depthmap(_p(velo), int(velo.shape[0]), _p(intr), _p(m_velo2cam),
+                                              int(width), int(height), int(filtering), float(filterdiff),
+                                              int(pool_scale), float(pool_default), _p(zbuf), _p(dmap),
+                                              _p(small), _p(mask), _stream()))
+    return dmap, small, mask
+
+
+def minpool(x, scale, default=0):
+    """minpool (reference utils/img_utils.py:87-95): [..., H, W] -> [..., H // scale, W // scale]."""
+    _need(x, "x")
+    x = x.contiguous()
+    H, W = x.shape[-2:]
+    n = x.numel() // (H * W)
+    out = torch.empty(tuple(x.shape[:-2]) + (H // scale, W // scale), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().dpv_minpool(_p(x), _p(out), n, H, W, int(scale), float(default), _stream()))
+    return out

@@ -19,6 +19,11 @@ def powerf(d_min, d_max, nDepth, power):
     return np.array([d_min + (d_max - d_min) * v for v in x])
 
 
+def minpool(tensor, scale, default=0):
+    """utils/img_utils.py:87-95."""
+    return ops.minpool(tensor, scale, default)
+
+
 def dpv_to_depthmap(dpv, d_candi, BV_log=False):
     if dpv.shape[0] != 1:
         raise Exception('Unable to handle this case')

@@ -191,3 +191,27 @@ def unc_rmse_case(name):
 
 
 UNC_RMSE_CASES = ["small", "full"]
+
+
+# ------------------------------------------------------------------ LiDAR depth maps
+def lidar_case(name):
+    """A synthetic Velodyne sweep in front of a KITTI-like camera: points on a ground plane, two walls
+    and a few boxes (so that the z-buffer sees occlusions and the filter sees depth steps), some behind
+    the camera, some outside the image."""
+    n, width, height, seed = {"small": (4000, 96, 64, 61), "kitti": (60000, 384, 256, 62),
+                              "sparse": (300, 52, 36, 63)}[name]
+    r = synth.rng(seed)
+    az = r.uniform(-np.pi, np.pi, n)
+    el = r.uniform(-0.43, 0.04, n)
+    rng_m = np.minimum(1.73 / np.maximum(np.tan(-el), 1e-3), r.choice([8.0, 15.0, 30.0, 60.0], n))
+    rng_m = rng_m * r.uniform(0.98, 1.02, n)
+    velo = np.stack([rng_m * np.cos(el) * np.cos(az), rng_m * np.cos(el) * np.sin(az), rng_m * np.sin(el),
+                     np.ones(n)], 1).astype(np.float32)
+    # velodyne (x fwd, y left, z up) -> camera (x right, y down, z fwd), small lever arm
+    M = np.array([[0, -1, 0, 0.02], [0, 0, -1, -0.08], [1, 0, 0, -0.27], [0, 0, 0, 1]], dtype=np.float32)
+    fx = 0.75 * width
+    intr = np.array([[fx, 0, width / 2.0, 0], [0, fx, height / 2.0, 0], [0, 0, 1, 0]], dtype=np.float32)
+    return dict(velo=velo, intr=intr, M=M, width=width, height=height, filtering=2, filterdiff=1.0)
+
+
+LIDAR_CASES = ["small", "kitti", "sparse"]
