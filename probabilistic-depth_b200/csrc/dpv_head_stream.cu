@@ -481,6 +481,15 @@ int launch_head_stream_plain(const HeadArgs& h, cudaStream_t st) {
     return hs_dispatch(a, h.D, h.mode, false, nullptr, st);
 }
 
+// dpv_head_uftile.cu: the tile form of the fused kernel (default for D = 32 / 64)
+long long head_uf_tile_workspace_floats(int B, int D, int H, int W);
+int launch_head_uf_tile(const float* x, const float* d, float* logp, float* depth, float* var, long long* argmax,
+                        float* quarter, const float* intr, const int* row_tab, const int* col_tab, float* uf,
+                        float* depth_zero, float* workspace, int B, int D, int H, int W, long long intr_bs,
+                        int mode, float zstart, float zend, float maxd, float mind, float pad_depth,
+                        cudaStream_t st);
+static const int g_head_uf_stream = [] { const char* e = getenv("DPV_HEAD_UF_STREAM"); return e ? atoi(e) : 0; }();
+
 }  // namespace dpv
 
 // ------------------------------------------------------------------------------------ C ABI
@@ -488,7 +497,8 @@ extern "C" int64_t dpv_head_ufield_workspace_floats(int B, int D, int H, int W) 
     dpv::HsPlan p;
     if (!dpv::hs_plan(B, D, H, W, true, &p)) return 0;
     const int64_t recs = (int64_t)p.G;
-    return recs * p.rec_floats + recs * dpv::HS_NW + 8;      // records, then per-warp flags (int32)
+    const int64_t stream_ws = recs * p.rec_floats + recs * dpv::HS_NW + 8;      // records, then per-warp flags (int32)
+    return std::max<int64_t>(stream_ws, dpv::head_uf_tile_workspace_floats(B, D, H, W));
 }
 
 // Host-side helper (no device work): turn the four nearest-shift index maps of dpv_ufield into the
@@ -557,6 +567,12 @@ extern "C" int dpv_head_ufield(const float* x, const float* d_candi, float* logp
     DPV_CHECK_ARG(in_mode == DPV_IN_LOGITS || in_mode == DPV_IN_LOGPROB);
     HsPlan p;
     if (!hs_plan(B, D, H, W, true, &p)) return DPV_E_UNSUPP;
+    if (!g_head_uf_stream) {   // tile kernel (dpv_head_uftile.cu) unless the shape is not one of its
+        const int rc = launch_head_uf_tile(x, d_candi, logp, depth, variance, (long long*)argmax, quarter, intr_up,
+                                           row_tab, col_tab, uf, depth_zero, workspace, B, D, H, W, intr_bstride,
+                                           in_mode, zstart, zend, maxd, mind, pad_depth, (cudaStream_t)stream);
+        if (rc != DPV_E_UNSUPP) return rc;
+    }
     HeadStreamArgs a = {};
     a.x = x; a.d = d_candi; a.logp = logp; a.depth = depth;
     a.var = variance; a.argmax = (long long*)argmax; a.quarter = quarter;
