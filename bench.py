@@ -206,7 +206,7 @@ def run_ours(args, dpv):
     B = WL["B"]
     hi = host_inputs(dpv, B, seed=rank)
     step = frame_mod.FrameStep(B, WL["V"], WL["C"], WL["D"], WL["h"], WL["w"], WL["H"], WL["W"], hi["d"],
-                               sigma=10.0, mode="default", device=dev, fuse_uf=args.fuse_uf,
+                               sigma=10.0, mode="default", device=dev, fuse_uf=not args.no_fuse_uf,
                                fuse_lsm=not args.no_fuse_lsm)
     # two input sets in HBM, alternated: 2 x 227 MB read + 227 MB written per step >> 126 MB L2
     nset = 2
@@ -297,7 +297,8 @@ def run_ours(args, dpv):
         achieved = head_bytes / (head_mean_ms * 1e-3) / 1e9
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "head_full_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "head_uf_tile_traffic.json" if step.fused_uf
+                                   else "head_full_traffic.json")) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -316,7 +317,12 @@ def run_ours(args, dpv):
             "roofline": {"kernel": head_name, "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": head_bytes, "ms_per_launch": head_mean_ms},
+                         "algorithmic_bytes_per_launch": head_bytes, "ms_per_launch": head_mean_ms,
+                         "note": ("fused K3+K5: bytes of the fused operation itself (logits in, log-DPV and the "
+                                  "per-pixel / per-column products out); SURVEY 8d counts K5 as a second pass "
+                                  "over the DPV, see unfused_bytes_frac") if step.fused_uf else "K3 alone",
+                         "unfused_bytes_frac": ((alg["head_full"] + alg["ufield"]) / (head_mean_ms * 1e-3) / 1e9 / peak)
+                         if step.fused_uf else None},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "dpv_pipeline_run (host buffers, pinned)"},
@@ -355,8 +361,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fuse-uf", action="store_true",
-                    help="run K3+K5 as the single fused TMA-fed kernel instead of dpv_head + dpv_ufield")
+    ap.add_argument("--no-fuse-uf", action="store_true",
+                    help="run K3 and K5 as dpv_head + dpv_ufield (4 launches) instead of the fused tile kernel")
     ap.add_argument("--no-fuse-lsm", action="store_true",
                     help="1/4-res log-softmax as its own dpv_head launch instead of the sweep kernel's epilogue")
     args = ap.parse_args()

@@ -147,9 +147,8 @@ extern "C" int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float
     PIPE_TRY(up(p->row_fwd, row_fwd, (int64_t)H * 4)); PIPE_TRY(up(p->row_inv, row_inv, (int64_t)H * 4));
     PIPE_TRY(up(p->col_fwd, col_fwd, (int64_t)W * 4)); PIPE_TRY(up(p->col_inv, col_inv, (int64_t)W * 4));
     // K3 + K5 in one pass when the shifts allow it (they do for the reference's row shifts)
-    // Item by item a persistent fused CTA would get only one or two rows; the fused kernel pays off
-    // for batched calls (FrameStep), so it is opt-in here.
-    static const bool want_fused = [] { const char* e = getenv("DPV_PIPELINE_FUSED_UF"); return e && atoi(e) != 0; }();
+    // (the tile form of the fused kernel has no per-item penalty; DPV_PIPELINE_FUSED_UF=0 switches it off)
+    static const bool want_fused = [] { const char* e = getenv("DPV_PIPELINE_FUSED_UF"); return !e || atoi(e) != 0; }();
     const bool fused = want_fused && (W % 4 == 0) && dpv_head_ufield_workspace_floats(1, D, H, W) > 0 &&
                        dpv_uf_fused_tables(row_fwd, row_inv, col_fwd, col_inv, H, W,
                                            p->h_row_tab.data(), p->h_col_tab.data()) == 0;

@@ -19,7 +19,7 @@ from . import _lib, ops
 
 class FrameStep:
     def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None,
-                 fuse_uf=False, fuse_lsm=True):
+                 fuse_uf=True, fuse_lsm=True):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dev = dev
         self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W = B, V, C, D, h, w, H, W
@@ -44,10 +44,10 @@ class FrameStep:
         # The epilogue needs all planes of a pixel in one CTA, i.e. no plane split: only when the batch
         # alone fills the machine (the launcher splits planes below 148 x 8 warps of pixels).
         self.fuse_lsm = bool(fuse_lsm) and (w % 4 == 0) and B * h * ((w + 31) // 32) >= 148 * 8
-        # K3 + K5 either as dpv_head followed by dpv_ufield (default: the short-CTA head kernel runs at
-        # ~85 % of the HBM roof and the UF pass re-reads only the road-band tiles) or in one pass with
-        # the persistent TMA-fed kernel (fuse_uf=True; same step time at 8 x 256 x 384, see
-        # profiles/README.md)
+        # K3 + K5 in one pass (fuse_uf, default: the tile kernel of dpv_head_uftile.cu takes gen_ufield's
+        # column sums while the probabilities are in registers: 0.094 ms per batch of 8 x 256 x 384) or as
+        # dpv_head followed by dpv_ufield's three launches (0.075 + 0.040 ms; also what shapes the fused
+        # kernel does not take fall back to)
         self.tabs = ops.uf_fused_tables(H, W, ops.KITTI_UF["pshift"], dev) if fuse_uf else None
         nfused = int(self.lib.dpv_head_ufield_workspace_floats(B, D, H, W)) if self.tabs else 0
         self.fused_uf = nfused > 0
@@ -169,6 +169,6 @@ class FrameStep:
         B, D, HW = self.B, self.D, self.H * self.W
         head = 8 * HW * D + 16 * HW
         if self.fused_uf:
-            return "dpv::head_stream_kernel<64,LOGITS,LOGP,UF> (full-res head + UF, fused, TMA-fed)", \
+            return "dpv::head_uf_tile_kernel<64,LOGITS,LOGP> + finish (full-res head + UF, fused)", \
                 B * (head + 4 * D * self.W + 4 * HW)
         return "dpv::head_kernel<64,1,LOGITS,...> (full-res head)", B * head

@@ -15,8 +15,8 @@ tail -2 $O/smoke.log
 echo "== bench"
 timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"
 timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"
-timeout 600 python bench.py --fuse-uf --no-cpu-baseline > $O/bench_n1_fused.json 2> $O/bench_n1_fused.err; echo "bench fused rc=$?"
-cat $O/bench_n1.json $O/bench_n1_fused.json $O/bench_ref.json
+timeout 600 python bench.py --no-fuse-uf --no-cpu-baseline > $O/bench_n1_unfused.json 2> $O/bench_n1_unfused.err; echo "bench unfused rc=$?"
+cat $O/bench_n1.json $O/bench_n1_unfused.json $O/bench_ref.json
 echo "== per-kernel"
 timeout 600 python tools/bench_kernels.py > $O/kernels.log 2>&1; echo "kernels rc=$?"
 timeout 600 python tools/bench_kernels.py --graph > $O/kernels_graph.log 2>&1; echo "kernels graph rc=$?"
@@ -27,7 +27,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/launches_bench.log 2>&1
 echo "launches rc=$?"
 echo "== ncu full"
-N=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'head_kernel|sweep|ufield|uf_' \
+N=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'head_kernel|head_uf|sweep|ufield|uf_' \
     -c 12 -f -o $O/prof_step python tools/run_once.py > $O/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 fi
