@@ -6,7 +6,7 @@
 // 8 x 256 x 384 (three UF launches that re-read the road-band third of the volume), and the persistent
 // TMA-fed kernel (dpv_head_stream.cu) fuses them at 0.110 ms -- its per-row read-modify-write of the
 // running sums in global memory and its one-wave schedule cost what the fusion saves.  Here a CTA owns
-// a tile of 32 columns x 8 rows; warp w takes rows w and w + 4 of the tile, so the four warps hold four
+// a tile of 32 columns x 8 rows; warp w takes rows w and w + 4 of the tile, so the four warps hold
 // rows of the SAME 32 columns and their partial column sums meet in shared memory:
 //   * per pixel: exactly dpv_head's arithmetic and outputs (log-softmax, E[d], Var, arg-max, 1/4
 //     hand-off), then the numerator / denominator weights of gen_ufield in closed form (the two
@@ -17,13 +17,15 @@
 //     flag; tiles off the band write nothing;
 //   * head_uf_tile_finish_kernel adds the flagged tiles of a column in row order and divides: no float
 //     atomics, bit-reproducible.
-// 6144 short CTAs per batch (8.3 waves of 740 resident) instead of one persistent wave.
+// 3072 short CTAs per batch (4.2 waves of 740 resident) instead of one persistent wave.  (4-row tiles,
+// one row per warp, measured the same: 0.094 vs 0.093 ms; packed fp32x2 arithmetic for the soft-max and
+// the moments cut the instruction count by a quarter and changed nothing: the kernel waits on memory.)
 #include "dpv_common.cuh"
 
 namespace dpv {
 
 constexpr int UT_NT = 128, UT_NW = 4;
-constexpr int UT_ROWS = 4;            // rows per tile (one per warp)
+constexpr int UT_ROWS = 8;            // rows per tile (two per warp)
 constexpr float kUtL2e = 1.4426950408889634f;
 constexpr float kUtLn2 = 0.6931471805599453f;
 
