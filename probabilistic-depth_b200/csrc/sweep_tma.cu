@@ -210,7 +210,6 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
     __shared__ float geo_s[16];                                        // K R (9), K t (3), cx, cy of the view
     __shared__ unsigned long long full_bar[TM_NSTAGE];
     __shared__ TmShared ts;
-    __shared__ float lsm_m[TM_PX], lsm_l[TM_PX];
 
     const int HW = a.H * a.W;
     const int kper = (a.D + a.PS - 1) / a.PS;
@@ -521,8 +520,9 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
 
     // ---------------- 5. result tile -> global memory, one 128-byte row per warp-instruction ----
     __syncthreads();
+    float lsm_m = 0.f, lsm_l = 0.f;   // per-column max and log-sum (lane = column in the copy-out too)
     if (a.lsm != nullptr) {   // log_softmax over the planes (host guarantees PS == 1)
-        float* red = stage0;   // [T][PX] partials; the stages are idle
+        float* red = stage0;   // [2][T][PX] partials; the stages are idle
         float m = -INFINITY;
         for (int k = t; k < nk; k += TM_T) m = fmaxf(m, out_s[k * TM_OS + px]);
         red[t * TM_PX + px] = m;
@@ -535,22 +535,19 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
         for (int k = t; k < nk; k += TM_T) sum += __expf(out_s[k * TM_OS + px] - m);
         red[(TM_T + t) * TM_PX + px] = sum;
         __syncthreads();
-        if (t == 0) {
-            sum = 0.f;
+        sum = 0.f;
 #pragma unroll
-            for (int u = 0; u < TM_T; ++u) sum += red[(TM_T + u) * TM_PX + px];
-            lsm_m[px] = m; lsm_l[px] = logf(sum);
-        }
-        __syncthreads();
+        for (int u = 0; u < TM_T; ++u) sum += red[(TM_T + u) * TM_PX + px];   // same order in every quarter
+        lsm_m = m; lsm_l = logf(sum);
     }
     {
-        const int col = tid & 31, x_out = tx * TM_PX + col;
+        const int col = px, x_out = tx * TM_PX + col;
         if (x_out < a.W) {
             const long long base = ((long long)b * a.D + k0) * HW + (long long)y * a.W + x_out;
-            for (int k = tid >> 5; k < nk; k += TM_NT / 32) {
+            for (int k = t; k < nk; k += TM_T) {
                 const float val = out_s[k * TM_OS + col];
                 a.cost[base + (long long)k * HW] = val;
-                if (a.lsm != nullptr) a.lsm[base + (long long)k * HW] = (val - lsm_m[col]) - lsm_l[col];
+                if (a.lsm != nullptr) a.lsm[base + (long long)k * HW] = (val - lsm_m) - lsm_l;
             }
         }
     }
