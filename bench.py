@@ -190,10 +190,14 @@ def run_ours(args, dpv):
         raise SystemExit("bench.py: no CUDA device; the DPV path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    out = sys.stdout
     if world > 1:
-        # NCCL writes its version / debug lines to stdout when NCCL_DEBUG is set in the environment;
-        # stdout carries exactly one JSON line, so send them to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version / debug lines on file descriptor 1 when NCCL_DEBUG is set in the
+        # environment (NCCL_DEBUG_FILE did not catch the version line on the GPU boxes).  stdout carries
+        # exactly one JSON line: keep a private copy of fd 1 for it and point fd 1 at stderr.
+        sys.stdout.flush()
+        out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -349,7 +353,7 @@ def run_ours(args, dpv):
             line["cpu_baseline"] = {
                 "value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                 "sample": "%d frame(s) of the batch-8 workload in %.1f s, torch CPU ops" % (n, dt)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
