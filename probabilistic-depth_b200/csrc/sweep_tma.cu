@@ -271,30 +271,31 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
         int my_run0;       // run that holds my first plane
         {
             unsigned long long starts = 0ull;
-            int n = 0, first_id = kTmNone, cur_id = kTmNone, cur_x = 0, cur_y = 0;
+            int n = 0, first_id = kTmNone, cur_id = kTmNone;
             int bx0 = 1 << 30, bx1 = -(1 << 30), by0 = 1 << 30, by1 = -(1 << 30);
             if (active) {
+                float cur_xf = 0.f, cur_yf = 0.f;   // origin of the current run's cell
+                bool in_cell = false;               // ... when it has one (not "outside")
                 for (int k = wa; k < wb; ++k) {
                     float ix, iy;
                     tm_coord<EXACT>(g, pt, d_s[k], ix, iy);
+                    // fast path: still inside the current cell (with the border slack)?  Covers "same
+                    // floor cell" too, so the floor / bounds / packing below run only where a run may start.
+                    const float fx = ix - cur_xf, fy = iy - cur_yf;
+                    if (in_cell && fx >= -kCellSlack && fx <= 1.0f + kCellSlack && fy >= -kCellSlack &&
+                        fy <= 1.0f + kCellSlack)
+                        continue;
                     const Tap tap = make_tap(ix, iy);
                     const bool inside = (tap.x0 >= -1) & (tap.x0 < a.W) & (tap.y0 >= -1) & (tap.y0 < a.H);
                     const int id = inside ? tm_pack(tap.x0, tap.y0) : kTmOutside;
-                    bool cont = (id == cur_id);
-                    if (!cont && cur_id >= 0) {   // inside a run with a real cell: border slack
-                        const float fx = ix - (float)cur_x, fy = iy - (float)cur_y;
-                        cont = fx >= -kCellSlack && fx <= 1.0f + kCellSlack && fy >= -kCellSlack &&
-                               fy <= 1.0f + kCellSlack;
-                    }
-                    if (!cont) {
-                        cur_id = id; cur_x = tap.x0; cur_y = tap.y0;
-                        starts |= 1ull << (k - wa);
-                        if (n == 0) first_id = id;
-                        ++n;
-                        if (inside) {
-                            bx0 = min(bx0, tap.x0); bx1 = max(bx1, tap.x0);
-                            by0 = min(by0, tap.y0); by1 = max(by1, tap.y0);
-                        }
+                    if (id == cur_id) continue;     // outside -> outside
+                    cur_id = id; cur_xf = (float)tap.x0; cur_yf = (float)tap.y0; in_cell = inside;
+                    starts |= 1ull << (k - wa);
+                    if (n == 0) first_id = id;
+                    ++n;
+                    if (inside) {
+                        bx0 = min(bx0, tap.x0); bx1 = max(bx1, tap.x0);
+                        by0 = min(by0, tap.y0); by1 = max(by1, tap.y0);
                     }
                 }
             }
