@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/dpv_b200.h"
 
@@ -133,6 +134,29 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Programmatic dependent launch (PDL).  A kernel launched with dpv_launch_pdl may become resident while
+// the previous kernel of the stream is still draining its last CTAs; pdl_wait() at its top blocks until
+// that kernel has completed and its writes are visible, so stream-order semantics are unchanged -- what
+// disappears is the launch latency / drain bubble between consecutive kernels (~2 us each on B200, three
+// per step).  pdl_wait() returns at once in a kernel that was launched normally, and after a kernel that
+// never triggers (cuDNN, torch) the dependent simply starts when that kernel's CTAs have exited.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dpv_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st, Args&&... args) {
+    static const bool off = [] { const char* e = getenv("DPV_NO_PDL"); return e && atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // Streaming global accesses: the big volumes are touched once, keep them out of L1.

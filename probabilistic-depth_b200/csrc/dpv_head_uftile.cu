@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(UT_NT, 5) head_uf_tile_kernel(const UtArgs a) 
     const int x_raw = blockIdx.x * 32 + lane;
     const bool live = x_raw < a.W;
     const int x = live ? x_raw : a.W - 1;     // dead lanes shadow the last column (never stored)
+    pdl_wait();       // (PDL) stream order: the producer of x has completed
+    pdl_trigger();
     for (int k = tid; k < D; k += UT_NT) d_s[k] = __ldg(a.d + k);
     __syncthreads();
     const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
@@ -225,6 +227,8 @@ __global__ void __launch_bounds__(256) head_uf_tile_finish_kernel(const UtArgs a
     const int k = blockIdx.y * 8 + g;
     const bool ok = x < a.W;
     const int xe = ok ? x : 0;
+    pdl_wait();       // (PDL) the tile kernel has completed: its partial sums and flags are visible
+    pdl_trigger();
     const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
     for (int ch = tid; ch < a.nchunk; ch += 256)
         on_s[ch] = (unsigned char)(__ldg(a.flag + ((long long)b * a.nchunk + ch) * a.xtiles + blockIdx.x) != 0);
@@ -283,15 +287,18 @@ template <int D>
 static int ut_launch(const UtArgs& a, int mode, cudaStream_t st) {
     dim3 grid(a.xtiles, a.nchunk, a.B), block(UT_NT);
     const bool lp = a.logp != nullptr;
+    cudaError_t e;
     if (mode == DPV_IN_LOGITS) {
-        if (lp) head_uf_tile_kernel<D, DPV_IN_LOGITS, true><<<grid, block, 0, st>>>(a);
-        else head_uf_tile_kernel<D, DPV_IN_LOGITS, false><<<grid, block, 0, st>>>(a);
+        e = lp ? dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGITS, true>, grid, block, 0, st, a)
+               : dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGITS, false>, grid, block, 0, st, a);
     } else {
-        if (lp) head_uf_tile_kernel<D, DPV_IN_LOGPROB, true><<<grid, block, 0, st>>>(a);
-        else head_uf_tile_kernel<D, DPV_IN_LOGPROB, false><<<grid, block, 0, st>>>(a);
+        e = lp ? dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGPROB, true>, grid, block, 0, st, a)
+               : dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGPROB, false>, grid, block, 0, st, a);
     }
+    if (e != cudaSuccess) return (int)e;
     DPV_LAUNCH_END();
-    head_uf_tile_finish_kernel<D><<<dim3(a.xtiles, (D + 7) / 8, a.B), 256, 0, st>>>(a);
+    e = dpv_launch_pdl(head_uf_tile_finish_kernel<D>, dim3(a.xtiles, (D + 7) / 8, a.B), dim3(256), 0, st, a);
+    if (e != cudaSuccess) return (int)e;
     DPV_LAUNCH_END();
     return 0;
 }
