@@ -6,13 +6,15 @@
 
 Workload (BASELINE.json configs[1]): default_stereo, batch 8 per GPU, D=64 bins, image
 256x384, features / cost volume 64x96, C=67 channels, V=1 source view, fp32.  One "step" pushes
-one batch of 8 frames through the hot-path kernels (cost volume, 1/4-res log-softmax, full-res
-head with E[d]/Var/argmax/hand-off, uncertainty field); the CNN blocks between them are cuDNN's
-and are not part of the path (their outputs are synthetic inputs here).
+one batch of 8 frames through the hot-path kernels: cost volume with the 1/4-res log-softmax in its
+epilogue, then the full-res head (log-softmax, E[d], Var, arg-max, 1/4 hand-off) fused with the
+uncertainty field -- three launches; the CNN blocks between them are cuDNN's and are not part of
+the path (their outputs are synthetic inputs here).
 `value`  : frames/s with every input already resident in HBM, device-timed, max over ranks.
 `e2e`    : frames/s through the host-buffer C-ABI pipeline (dpv_pipeline_run): pinned host
            inputs are copied in, results copied back, inside the timed region.
-`roofline`: the dominant kernel (full-res head) against the measured HBM peak.
+`roofline`: the dominant kernel (fused full-res head + UF; --no-fuse-uf: the head alone) against the
+           measured HBM peak; `kernels` / `sweep`: per-kernel times and the sweep's FP32 figures.
 `cpu_baseline` / --impl reference: the CPU port of the reference's PyTorch path (oracle/) on the
            host cores, bounded sample.
 """
