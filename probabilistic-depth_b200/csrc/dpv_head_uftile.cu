@@ -99,8 +99,7 @@ __global__ void __launch_bounds__(UT_NT, 5) head_uf_tile_kernel(const UtArgs a) 
     const int x_raw = blockIdx.x * 32 + lane;
     const bool live = x_raw < a.W;
     const int x = live ? x_raw : a.W - 1;     // dead lanes shadow the last column (never stored)
-    pdl_wait();       // (PDL) stream order: the producer of x has completed
-    pdl_trigger();
+    pdl_trigger();    // (PDL) the finish kernel may become resident behind our last CTAs
     for (int k = tid; k < D; k += UT_NT) d_s[k] = __ldg(a.d + k);
     __syncthreads();
     const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
@@ -228,7 +227,6 @@ __global__ void __launch_bounds__(256) head_uf_tile_finish_kernel(const UtArgs a
     const bool ok = x < a.W;
     const int xe = ok ? x : 0;
     pdl_wait();       // (PDL) the tile kernel has completed: its partial sums and flags are visible
-    pdl_trigger();
     const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
     for (int ch = tid; ch < a.nchunk; ch += 256)
         on_s[ch] = (unsigned char)(__ldg(a.flag + ((long long)b * a.nchunk + ch) * a.xtiles + blockIdx.x) != 0);
@@ -289,14 +287,14 @@ static int ut_launch(const UtArgs& a, int mode, cudaStream_t st) {
     const bool lp = a.logp != nullptr;
     cudaError_t e;
     if (mode == DPV_IN_LOGITS) {
-        e = lp ? dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGITS, true>, grid, block, 0, st, a)
-               : dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGITS, false>, grid, block, 0, st, a);
+        if (lp) head_uf_tile_kernel<D, DPV_IN_LOGITS, true><<<grid, block, 0, st>>>(a);
+        else head_uf_tile_kernel<D, DPV_IN_LOGITS, false><<<grid, block, 0, st>>>(a);
     } else {
-        e = lp ? dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGPROB, true>, grid, block, 0, st, a)
-               : dpv_launch_pdl(head_uf_tile_kernel<D, DPV_IN_LOGPROB, false>, grid, block, 0, st, a);
+        if (lp) head_uf_tile_kernel<D, DPV_IN_LOGPROB, true><<<grid, block, 0, st>>>(a);
+        else head_uf_tile_kernel<D, DPV_IN_LOGPROB, false><<<grid, block, 0, st>>>(a);
     }
-    if (e != cudaSuccess) return (int)e;
     DPV_LAUNCH_END();
+    // (PDL) the finish kernel becomes resident behind the tile kernel's last CTAs and waits for them
     e = dpv_launch_pdl(head_uf_tile_finish_kernel<D>, dim3(a.xtiles, (D + 7) / 8, a.B), dim3(256), 0, st, a);
     if (e != cudaSuccess) return (int)e;
     DPV_LAUNCH_END();

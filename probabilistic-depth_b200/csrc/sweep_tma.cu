@@ -225,8 +225,6 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
     const bool active = x < a.W;
     const int p = active ? y * a.W + x : y * a.W;
     if (nk <= 0) return;
-    pdl_wait();       // (PDL) the previous kernel of the stream has completed
-    pdl_trigger();    // ... and the next one may become resident behind our last wave
     for (int k = tid; k < nk; k += TM_NT) d_s[k] = __ldg(a.d + k0 + k);
     if (tid == 0) {
 #pragma unroll
@@ -632,13 +630,11 @@ int launch_sweep_gram_tma(const SweepArgs& a, cudaStream_t st) {
     if (exact) {
         e = cudaFuncSetAttribute(sweep_gram_tma_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        e = dpv_launch_pdl(sweep_gram_tma_kernel<4, true>, grid, block, smem, st, a, msrc, mref);
-        if (e != cudaSuccess) return (int)e;
+        sweep_gram_tma_kernel<4, true><<<grid, block, smem, st>>>(a, msrc, mref);
     } else {
         e = cudaFuncSetAttribute(sweep_gram_tma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        e = dpv_launch_pdl(sweep_gram_tma_kernel<4, false>, grid, block, smem, st, a, msrc, mref);
-        if (e != cudaSuccess) return (int)e;
+        sweep_gram_tma_kernel<4, false><<<grid, block, smem, st>>>(a, msrc, mref);
     }
     DPV_LAUNCH_END();
     return 0;

@@ -133,6 +133,22 @@ class FrameStep:
                                   B, D, H, W, 9, ops.IN_LOGPROB, *self.uf_params, self.pad_depth, st))
         hk("ufield", 1)
 
+    def capture(self, *args, **kw):
+        """Record one step on these (fixed) input tensors into a CUDA graph; `graph.replay()` then
+        re-runs it with a single launch from the host.  Every buffer the step touches is owned by the
+        caller or pre-allocated here, so the graph holds no allocations."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):      # warm-up outside the capture (module loading, attributes)
+            self.run(*args, **kw)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(*args, **kw)
+        return g
+
     def launches_per_step(self):
         # sweep, 1/4-res soft-max, head, UF (weights + partial sums + finish); fused: stream kernel + finish
         n = {"default": 6, "upsample": 7, "feedback": 8}[self.mode]
