@@ -246,3 +246,37 @@ def test_large_d_plane_sharded_sweep_full_resolution(dpv, D, world, h, w):
     logp, depth, var, amax = _merge_plane_shards(sh, full, d, world)
     assert float(torch.logsumexp(logp, 1).abs().max()) < 1e-4
     assert torch.equal(amax, torch.argmax(full, 1))
+
+
+# ----------------------------------------------------------------- CUDA-graph replay of the step
+@pytest.mark.parametrize("mode", ["default", "feedback"])
+def test_frame_step_graph_replay_is_bit_identical(dpv, mode):
+    """FrameStep.capture(): a replayed step writes exactly what the call-by-call step writes, also after
+    the inputs changed in place (the graph holds pointers, not values)."""
+    B, V, C, D, h, w, H, W = 2, 1, 67, 64, 16, 24, 64, 96
+    d, cam, feats, poses, logits = _inputs(dpv, B, V, C, D, h, w, H, W, seed=900)
+    step = frame_mod().FrameStep(B, V, C, D, h, w, H, W, d, mode=mode)
+    args = [cu(feats), cu(poses), cu(cam["intrinsics"]), cu(cam["unit_ray"]), cu(logits), cu(cam["intrinsics_up"])]
+    kw = {}
+    if mode == "feedback":
+        kw = dict(feat_raw=cu(dpv.synth.randn(901, B, V + 1, D, h, w)),
+                  bv_resi=cu((0.5 * dpv.synth.randn(902, B, D, h, w)).astype(np.float32)))
+    g = step.capture(*args, **kw)
+    names = ["cost", "bv", "refined", "depth", "var", "argmax", "quarter", "uf", "dz"] + \
+        (["warped", "bv_upd"] if mode == "feedback" else [])
+    for trial in range(2):
+        if trial == 1:       # new values in the same buffers
+            args[0].copy_(cu(dpv.synth.randn(903, B, V + 1, C, h, w)))
+            args[4].mul_(0.5)
+        step.run(*args, **kw)
+        torch.cuda.synchronize()
+        want = {n: getattr(step, n).clone() for n in names}
+        for n in names:
+            getattr(step, n).fill_(0)
+        g.replay()
+        torch.cuda.synchronize()
+        for n in names:
+            a, b = getattr(step, n), want[n]
+            same = torch.equal(a, b) if a.dtype != torch.float32 else \
+                torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+            assert same, (mode, trial, n)
