@@ -150,8 +150,9 @@ int dpv_ufield(const float* dpv, const float* depth, const float* d_candi, const
  * models/models.py:351, trainer/default_trainer.py:221-222,333-336) and gen_ufield
  * (utils/img_utils.py:268-358) in one read of x [B,D,H,W] (in_mode DPV_IN_LOGITS or DPV_IN_LOGPROB):
  * the trainer calls them back to back on the refined DPV (trainer/default_trainer.py:232-244).
- * No ground-truth mask (that variant is dpv_ufield).  D in {32,64,128,256}, W % 4 == 0, else
- * DPV_E_UNSUPP.  row_tab [H][4] / col_tab [W] int32 DEVICE tables: build them on the host with
+ * No ground-truth mask (that variant is dpv_ufield).  D in {16,32,64}, W % 4 == 0, else
+ * DPV_E_UNSUPP (D = 32 / 64 run the tile kernel of dpv_head_uftile.cu, D = 16 the persistent
+ * TMA-fed kernel of dpv_head_stream.cu).  row_tab [H][4] / col_tab [W] int32 DEVICE tables: build them on the host with
  * dpv_uf_fused_tables from the same four index maps dpv_ufield takes (HOST pointers there), which
  * returns DPV_E_UNSUPP when the shifts do not compose to "same pixel or padding".
  * Any of logp / depth / variance / argmax / quarter / depth_zero may be null.

@@ -280,3 +280,29 @@ def test_frame_step_graph_replay_is_bit_identical(dpv, mode):
             same = torch.equal(a, b) if a.dtype != torch.float32 else \
                 torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
             assert same, (mode, trial, n)
+
+
+# ----------------------------------------------------------------- fused head + UF: other shapes
+@pytest.mark.parametrize("D,H,W", [(64, 60, 100), (32, 64, 96), (32, 44, 68), (16, 64, 96), (64, 256, 384)])
+def test_fused_head_ufield_equals_two_kernel_path(dpv, D, H, W):
+    """dpv_head_ufield (tile kernel for D = 32 / 64, the persistent kernel for D = 16) against dpv_head +
+    dpv_ufield on ragged shapes: widths that are not a multiple of the 32-column tile, heights that are not a
+    multiple of the 8-row tile.  Same per-pixel decisions (depth_zero, NaN pattern), same sums up to order."""
+    B = 2
+    s = dpv.synth
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(max(W // 4, 1), max(H // 4, 1), B)
+    x = cu(s.ground_plane_logits(40 + D, B, H, W, d, cam["intrinsics_up"][0]))
+    Ku = cu(cam["intrinsics_up"])
+    fused = dpv.ops.head_ufield(x, d, Ku, logp=True, depth=True, variance=True, argmax=True, quarter=True)
+    plain = dpv.ops.head(x, d, logp=True, depth=True, variance=True, argmax=True, quarter=True)
+    assert torch.equal(fused["argmax"], plain["argmax"])
+    assert torch.equal(fused["quarter"], fused["logp"][:, :, ::4, ::4][:, :, :H // 4, :W // 4])
+    for k in ("logp", "depth", "variance"):
+        assert scaled_err(fused[k], plain[k]) < 1e-5, k
+    uf2, dz2 = dpv.ops.ufield(fused["logp"], d, Ku, depth=fused["depth"])
+    assert torch.equal(fused["depth_zero"], dz2)
+    assert torch.equal(torch.isnan(fused["uf"]), torch.isnan(uf2))
+    ok = ~torch.isnan(uf2)
+    assert int(ok.sum()) > 0
+    assert float(((fused["uf"][ok] - uf2[ok]).abs() / uf2[ok].abs().clamp_min(1e-6)).max()) < 1e-5
