@@ -175,6 +175,27 @@ def run_reference(args, dpv):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers
+    of the end-to-end path are allocated (first touch) on the memory next to that GPU.  With one process per
+    GPU on a two-socket host, unbound ranks otherwise push half of their H2D traffic across the socket link.
+    Best effort: returns the number of CPUs bound to, or 0."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def alg_of(name, alg):
     """Algorithmic bytes of the launch(es) timed under `name` (FrameStep.algorithmic_bytes keys)."""
     return {"sweep": alg.get("sweep", 0), "head_quarter": alg.get("head_quarter", 0),
@@ -192,6 +213,7 @@ def run_ours(args, dpv):
         raise SystemExit("bench.py: no CUDA device; the DPV path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bound_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     out = sys.stdout
     if world > 1:
         # NCCL prints its version / debug lines on file descriptor 1 when NCCL_DEBUG is set in the
@@ -340,6 +362,7 @@ def run_ours(args, dpv):
                        "algorithmic_bytes_per_step": alg,
                        "uf_fused_into_head": bool(step.fused_uf),
                        "cuda_graph_replay": graphs is not None,
+                       "cpus_bound_per_rank": bound_cpus,
                        "quarter_log_softmax_in_sweep_epilogue": bool(step.fuse_lsm),
                        "frame_hbm_frac": sum(alg.values()) / (ms / args.steps * 1e-3) / 1e9 / peak,
                        "frame_hbm_frac_note": "SURVEY 8d bytes/frame (K5 counted as its own pass) / time / peak"},
