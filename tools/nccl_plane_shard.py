@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""configs[4] over real NCCL: depth-plane-sharded sweep + soft-max statistics all-reduce, one rank per GPU.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/nccl_plane_shard.py
+Every rank owns D/N planes of the cost volume (features replicated), PlaneShardedHead exchanges the per-pixel
+max / sums / central moment (NCCL all-reduce on the kernels' stream); each rank then checks its planes of the
+log-softmax and the replicated E[d] / Var / arg-max against the unsharded computation on its own GPU."""
+import importlib, os, sys
+import numpy as np, torch
+import torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+out = os.fdopen(os.dup(1), "w"); os.dup2(2, 1)       # NCCL's own prints go to stderr
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dpv = importlib.import_module("probabilistic-depth_b200")
+sh = importlib.import_module("probabilistic-depth_b200.sharding")
+s = dpv.synth
+cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+ok = True
+for D, h, w in ((128, 96, 320), (256, 384, 1280)):
+    B, C = 1, 16
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(w, h, B)
+    feats = cu(s.randn(800 + D, B, 2, C, h, w))
+    poses = cu(s.mono_poses(B).astype(np.float32))
+    K, rays = cu(cam["intrinsics"]), cu(cam["unit_ray"])
+    cost_local, (lo, hi) = sh.plane_sharded_sweep(feats[:, -1], feats[:, :-1], poses[:, :-1], K, rays, d, 10.0, rank, world)
+    head = sh.PlaneShardedHead(D)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = head(cost_local, d)                      # warm-up (communicator set-up)
+    torch.cuda.synchronize(); dist.barrier()
+    t0.record(); res = head(cost_local, d); t1.record(); torch.cuda.synchronize()
+    full = dpv.ops.sweep_cost_volume(feats[:, -1], feats[:, :-1], poses[:, :-1], K, rays, d, 10.0)
+    one = dpv.ops.head(full, d, logp=True, depth=True, variance=True, argmax=True)
+    def err(a, b): return float(((a - b).abs() / b.abs().clamp_min(1.0)).max())
+    e = dict(logp=err(res["logp"], one["logp"][:, lo:hi]), depth=err(res["depth"], one["depth"]),
+             var=err(res["variance"], one["variance"]), argmax_equal=bool(torch.equal(res["argmax"], one["argmax"])))
+    good = e["logp"] < 1e-4 and e["depth"] < 1e-4 and e["var"] < 1e-4
+    # arg-max: the shards' cost values differ from the unsharded launch by fp32 rounding, so compare on the margin
+    if not e["argmax_equal"]:
+        top2 = torch.topk(full, 2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+        good = good and bool(torch.equal(res["argmax"][clear], one["argmax"][clear]))
+    ok = ok and good
+    print("rank %d/%d D=%d %dx%d planes [%d,%d): %s  sharded head %.3f ms  %s" %
+          (rank, world, D, h, w, lo, hi, e, t0.elapsed_time(t1), "OK" if good else "MISMATCH"), file=out, flush=True)
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("ALL RANKS OK" if int(flag) == 1 else "FAILED", file=out, flush=True)
+dist.destroy_process_group()
+sys.exit(0 if int(flag) == 1 else 1)
