@@ -141,6 +141,17 @@ class PlaneShardedHead:
         self.lo, self.hi = plane_range(self.D, self.rank, self.world)
         self.local = local if local is not None else CudaShardKernels()
 
+    def _local_bins(self, d_candi, device):
+        """This rank's slice of the (global) bin depths on the device; uploaded once per bin vector."""
+        key = (id(d_candi) if not isinstance(d_candi, np.ndarray) else d_candi.ctypes.data, len(d_candi), str(device))
+        hit = getattr(self, "_bins_cache", None)
+        d_all = np.asarray(d_candi, dtype=np.float64).astype(np.float32)
+        if hit is not None and hit[0] == key and np.array_equal(hit[1], d_all):
+            return hit[2]
+        t = torch.from_numpy(np.ascontiguousarray(d_all[self.lo:self.hi])).to(device)
+        self._bins_cache = (key, d_all, t)
+        return t
+
     def _all_reduce(self, t, op):
         if self.world > 1:
             self.dist.all_reduce(t, op=op, group=self.group)
@@ -152,21 +163,25 @@ class PlaneShardedHead:
         if Dl != self.hi - self.lo:
             raise ValueError("rank %d owns %d planes, got %d" % (self.rank, self.hi - self.lo, Dl))
         x = x_local.contiguous().reshape(B, Dl, H * W)
-        d_all = np.asarray(d_candi, dtype=np.float64).astype(np.float32)
-        d_local = torch.from_numpy(np.ascontiguousarray(d_all[self.lo:self.hi])).to(x.device)
+        d_local = self._local_bins(d_candi, x.device)
         m, am = self.local.local_max(x, self.lo, argmax)
         out = {}
         if argmax:
             if self.world > 1:
+                # one all-gather of (max, arg-max) per rank serves both the arg-max merge and the global
+                # maximum (no separate MAX all-reduce)
                 cand = torch.stack([m, am]).contiguous()
                 gathered = [torch.empty_like(cand) for _ in range(self.world)]
                 dist.all_gather(gathered, cand, group=self.group)
                 vals = torch.stack([g[0] for g in gathered]).contiguous()
                 idx = torch.stack([g[1] for g in gathered]).contiguous()
+                gmax = vals.max(dim=0).values.contiguous()
             else:
                 vals, idx = m.unsqueeze(0).contiguous(), am.unsqueeze(0).contiguous()
+                gmax = m
             out["argmax"] = self.local.argmax_merge(vals, idx).reshape(B, H, W)
-        gmax = self._all_reduce(m.clone(), dist.ReduceOp.MAX)
+        else:
+            gmax = self._all_reduce(m.clone(), dist.ReduceOp.MAX)
         gsums = self._all_reduce(self.local.local_sums(x, d_local, gmax), dist.ReduceOp.SUM)
         gcentral = None
         if variance:
