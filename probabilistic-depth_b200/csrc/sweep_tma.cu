@@ -389,6 +389,11 @@ sweep_gram_tma_kernel(const SweepArgs a, const __grid_constant__ CUtensorMap map
                 const int s = q_issue % TM_NSTAGE;
                 ++q_issue;
                 float* st = stage0 + s * TM_STAGE;
+                // The stage area is also written through the generic proxy (run-list stitching, the Gram
+                // exchange, the soft-max partials) and read by all lanes; those accesses are ordered before
+                // this point by __syncthreads, and this fence orders them before the async-proxy writes of
+                // the bulk copies below.
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tm_mbar_expect_tx(&full_bar[s], (unsigned)((wh * TM_ROW + TM_CK * TM_PX) * sizeof(float)));
                 for (int r = 0; r < wh; ++r)
                     tm_load_5d(st + r * TM_ROW, &map_src, wx0, wy0 + r, chunk * TM_CK, v, b, &full_bar[s]);
