@@ -16,8 +16,8 @@
  *  - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the call returns.
  *  - Return value: 0 on success, a positive cudaError_t on a CUDA failure, a negative
  *    DPV_E_* code on a bad argument.  dpv_error_string() explains either.
- *  - Inputs are never modified.  No global mutable state; safe to call from one host thread
- *    per device/stream.
+ *  - Inputs are never modified.  No global mutable state besides one atomic launch counter
+ *    (dpv_launch_count); safe to call from one host thread per device/stream.
  *  - There is no CPU implementation behind any of these.
  */
 #ifndef DPV_B200_H_
@@ -105,7 +105,8 @@ int dpv_warp_feature(const float* feat, const float* pose, const float* K, const
  *   argmax   [B,H,W]    int64 first maximal bin of logp       (torch.argmax; not in the reference)
  *   quarter  [B,D,H/4,W/4] logp at rows/cols 0,4,8,...        trainer/default_trainer.py:221-222
  * in_mode: DPV_IN_LOGITS / DPV_IN_LOGPROB / DPV_IN_PROB (the last two skip the soft-max;
- * logp then echoes log-probabilities).  addend may be null.  d_candi [D] fp32.
+ * logp then echoes log-probabilities).  addend may be null and must be null unless in_mode is
+ * DPV_IN_LOGITS (DPV_E_BADARG otherwise).  d_candi [D] fp32.
  */
 int dpv_head(const float* x, const float* addend, const float* d_candi,
              float* logp, float* prob, float* depth, float* variance, int64_t* argmax,
@@ -134,6 +135,10 @@ int dpv_bayes_fuse(const float* bv, const float* prior, const float* dmaps, cons
  * row_fwd/row_inv [H], col_fwd/col_inv [W]: int32 source index of the +pshift / -pshift
  * nearest-neighbour shifts (-1 = samples zero padding), built once per shape by the host
  * wrapper from the reference's own grid construction.
+ * quash_range > 0 selects the quash_limit branch (utils/img_utils.py:325-332, taken for ILIM data and
+ * for every `cfgx` caller, ros/ros_net.py:279): a shifted-frame pixel keeps its weight only when its
+ * masked depth (zeros -> 1000) lies strictly within +/- quash_range (the reference uses 1.0) of the
+ * minimum of its column; 0 = the KITTI branch.
  * Outputs uf [B,D,W] (0/0 = NaN as in the reference) and depth_zero [B,H,W].
  * workspace: dpv_ufield_workspace_floats(B, D, H, W) floats.
  */
@@ -143,7 +148,7 @@ int dpv_ufield(const float* dpv, const float* depth, const float* d_candi, const
                const int* col_inv, float* uf, float* depth_zero, float* workspace,
                int B, int D, int H, int W, int64_t intr_bstride, int in_mode,
                float zstart, float zend, float maxd, float mind, float pad_depth,
-               void* stream);
+               float quash_range, void* stream);
 
 /* ---- K3 + K5 fused : depth-bin head with the uncertainty field accumulated in the same pass ----
  * dpv_head (log-softmax, E[d], Var, arg-max, 1/4 hand-off; utils/img_utils.py:52-61,

@@ -221,13 +221,19 @@ def depth_to_points(depth, intr):
     return torch.cat([(xf * d).unsqueeze(0), (yf * d).unsqueeze(0), d.unsqueeze(0)], 0)
 
 
+def cfgx_params(cfgx):
+    """utils/img_utils.py:269-275: parameters of a `cfgx` call (ros/ros_net.py:279)."""
+    return dict(pshift=cfgx["unc_ang"], zstart=cfgx["unc_shift"], zend=cfgx["unc_shift"] + cfgx["unc_span"],
+                maxd=100.0, mind=3.0, quash_limit=True)
+
+
 def uncertainty_field(dpv, d_candi, intr_up, log=True, mask=None, params=None):
     """Road-surface uncertainty-field collapse (utils/img_utils.py:268-358).
 
     dpv [1,D,H,W] (log-probabilities when log=True); intr_up [3,3]; optional
-    mask [1,H,W].  params defaults to the KITTI constants (:277-283).  The
-    quash_limit branch (ILIM data, :325-332) is not part of the hot path.
-    Returns (UF [1,D,W], depth * mask [1,H,W]).
+    mask [1,H,W].  params defaults to the KITTI constants (:277-283); params["quash_limit"]
+    (the `cfgx` caller ros/ros_net.py:279 and ILIM data, :269-275,289-290) adds the column gate of
+    :325-332.  Returns (UF [1,D,W], depth * mask [1,H,W]).
     """
     p = dict(KITTI_UF if params is None else params)
     pshift, zstart, zend, maxd, mind = p["pshift"], p["zstart"], p["zend"], p["maxd"], p["mind"]
@@ -248,6 +254,11 @@ def uncertainty_field(dpv, d_candi, intr_up, log=True, mask=None, params=None):
         else:
             ms = mask.clone()
         zmask = zmask * ms.squeeze(0)
+    if p.get("quash_limit", False):                       # :325-332
+        cleaned = (depth_s * zmask).squeeze(0)
+        cleaned[cleaned == 0] = 1000
+        col_min, _ = torch.min(cleaned, dim=0)
+        zmask = zmask * ((cleaned > col_min - 1.0) & (cleaned < col_min + 1.0)).float()
     if pshift != 0:
         zmask_p = F.grid_sample(zmask.unsqueeze(0).unsqueeze(0), g_inv, mode="nearest",
                                 align_corners=False).squeeze(0).squeeze(0)

@@ -27,7 +27,7 @@ PROTOTYPES = {
     "dpv_lidar_prior": (_c_i, [_c_fp] * 4 + [_c_i] * 4 + [_c_f, _c_fp]),
     "dpv_bayes_fuse": (_c_i, [_c_fp] * 7 + [_c_i] * 4 + [_c_f, _c_fp]),
     "dpv_ufield_workspace_floats": (_c_i64, [_c_i] * 4),
-    "dpv_ufield": (_c_i, [_c_fp] * 12 + [_c_i] * 4 + [_c_i64, _c_i] + [_c_f] * 5 + [_c_fp]),
+    "dpv_ufield": (_c_i, [_c_fp] * 12 + [_c_i] * 4 + [_c_i64, _c_i] + [_c_f] * 6 + [_c_fp]),
     "dpv_head_ufield_workspace_floats": (_c_i64, [_c_i] * 4),
     "dpv_uf_fused_tables": (_c_i, [_c_fp] * 4 + [_c_i] * 2 + [_c_fp] * 2),
     "dpv_head_ufield": (_c_i, [_c_fp] * 13 + [_c_i] * 4 + [_c_i64, _c_i] + [_c_f] * 5 + [_c_fp]),

@@ -2,12 +2,12 @@
 #include "dpv_common.cuh"
 
 namespace dpv {
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};   // the one piece of mutable library state: a relaxed counter
 }
 
-extern "C" int dpv_abi_version(void) { return 1; }
+extern "C" int dpv_abi_version(void) { return 2; }
 
-extern "C" long long dpv_launch_count(void) { return dpv::g_launch_count; }
+extern "C" long long dpv_launch_count(void) { return dpv::g_launch_count.load(std::memory_order_relaxed); }
 
 extern "C" const char* dpv_error_string(int code) {
     switch (code) {

@@ -4,15 +4,16 @@
 #include <stdint.h>
 #include <math.h>
 #include <stdlib.h>
+#include <atomic>
 
 #include "../../include/dpv_b200.h"
 
 namespace dpv {
 
-extern long long g_launch_count;   // defined in capi.cu; bumped by every launcher
+extern std::atomic<long long> g_launch_count;   // defined in capi.cu; bumped by every launcher
 
 #define DPV_CHECK_ARG(cond) do { if (!(cond)) return DPV_E_BADARG; } while (0)
-#define DPV_LAUNCH_END() do { ::dpv::g_launch_count++; cudaError_t e__ = cudaGetLastError(); \
+#define DPV_LAUNCH_END() do { ::dpv::g_launch_count.fetch_add(1, std::memory_order_relaxed); cudaError_t e__ = cudaGetLastError(); \
                               if (e__ != cudaSuccess) return (int)e__; } while (0)
 
 // ------------------------------------------------------------------ plane-sweep geometry

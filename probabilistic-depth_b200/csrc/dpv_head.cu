@@ -329,6 +329,7 @@ extern "C" int dpv_head(const float* x, const float* addend, const float* d_cand
     DPV_CHECK_ARG(x && d_candi);
     DPV_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0);
     DPV_CHECK_ARG(in_mode >= DPV_IN_LOGITS && in_mode <= DPV_IN_PROB);
+    DPV_CHECK_ARG(addend == nullptr || in_mode == DPV_IN_LOGITS);   // x + addend is a logits-only notion
     if (B > 65535) return DPV_E_UNSUPP;
     HeadArgs a;
     a.x = x; a.addend = addend; a.d = d_candi; a.logp = logp; a.prob = prob; a.depth = depth;

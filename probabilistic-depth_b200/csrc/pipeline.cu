@@ -190,7 +190,7 @@ extern "C" int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float
         PIPE_RC(dpv_ufield(p->refined + i * D * HW, p->depth + i * HW, p->d, p->intr + i * 9, nullptr,
                            p->row_fwd, p->row_inv, p->col_fwd, p->col_inv, p->uf + (int64_t)i * D * W,
                            p->dz + i * HW, p->ws + i * p->ws_floats_per_item, 1, D, H, W, 0,
-                           DPV_IN_LOGPROB, 0.6f, 0.6f + 0.3f, 100.f, 0.f, pad_depth, p->s_run));
+                           DPV_IN_LOGPROB, 0.6f, 0.6f + 0.3f, 100.f, 0.f, pad_depth, 0.f, p->s_run));
         }
         PIPE_TRY(cudaEventRecord(p->e_done[i], p->s_run));
         PIPE_TRY(cudaStreamWaitEvent(p->s_out, p->e_done[i], 0));

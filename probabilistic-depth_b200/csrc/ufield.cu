@@ -20,10 +20,10 @@ namespace dpv {
 struct UfArgs {
     const float* dpv; const float* depth; const float* d; const float* intr; const float* mask;
     const int* row_fwd; const int* row_inv; const int* col_fwd; const int* col_inv;
-    float* uf; float* depth_zero; float* part; float* cnt; float* wmap;
+    float* uf; float* depth_zero; float* part; float* cnt; float* wmap; float* colmin;
     int B, D, H, W, mode, rows_per_chunk, nchunk;
     long long intr_bs;
-    float zstart, zend, maxd1, mind, pad_depth;
+    float zstart, zend, maxd1, mind, pad_depth, quash;
 };
 
 // Weight of shifted-frame pixel (ys, xs): 1 when its back-projected point lies in the height
@@ -31,20 +31,69 @@ struct UfArgs {
 // the shifted ground-truth mask when one is given (:317-322).
 // (sy, yf) are properties of the shifted row ys alone -- its source row and (ys - cy) / fy -- and
 // are evaluated once per row of the chunk, not once per pixel.
+// `zc` receives the "cleaned" shifted depth of the quash_limit branch (:327-328): depth * weight with
+// exact zeros replaced by 1000.
 __device__ __forceinline__ float band_weight(const UfArgs& a, const float* __restrict__ depth_b,
-                                             const float* __restrict__ mask_b, int sy, float yf, int sx) {
+                                             const float* __restrict__ mask_b, int sy, float yf, int sx,
+                                             float* zc = nullptr) {
     const bool inside = (sy >= 0) & (sx >= 0);
     const float z = inside ? __ldg(depth_b + sy * a.W + sx) : a.pad_depth;
     const float yy = __fmul_rn(yf, z);
     const bool out = (yy > a.zend) || (yy < a.zstart) || (z > a.maxd1) || (z < a.mind);
     float w = out ? 0.f : 1.f;
     if (mask_b != nullptr) w = __fmul_rn(w, inside ? __ldg(mask_b + sy * a.W + sx) : 0.f);
+    if (zc != nullptr) {
+        const float c = __fmul_rn(z, w);
+        *zc = (c == 0.f) ? 1000.f : c;
+    }
     return w;
+}
+
+// quash_limit (:325-332): a shifted-frame pixel keeps its weight only when its cleaned depth lies
+// strictly within +/- quash of the minimum of its column.  `cmin` is that column minimum.
+__device__ __forceinline__ float quashed_weight(const UfArgs& a, const float* __restrict__ depth_b,
+                                                const float* __restrict__ mask_b, int sy, float yf, int sx,
+                                                float cmin) {
+    float zc;
+    const float w = band_weight(a, depth_b, mask_b, sy, yf, sx, &zc);
+    const bool keep = (zc > __fsub_rn(cmin, a.quash)) && (zc < __fadd_rn(cmin, a.quash));
+    return __fmul_rn(w, keep ? 1.f : 0.f);
 }
 
 constexpr int UF_COLS = 32;    // columns per CTA (one warp-width: 128 B rows of the volume)
 constexpr int UF_GROUPS = 8;   // warps per CTA, each owning D/8 consecutive bins
 constexpr int UF_ROWS = 32;    // image rows per CTA (one partial sum per chunk of rows)
+
+// Kernel 0 (quash_limit only): minimum of the cleaned shifted depth along every shifted-frame column
+// (torch.min over axis 0, :329; a NaN in the column makes the minimum NaN, as torch's min does).
+// One CTA = 32 columns of one item, the 8 warps stride over the rows.
+__global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_colmin_kernel(const UfArgs a) {
+    __shared__ float m_s[UF_GROUPS][UF_COLS];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int x = blockIdx.x * UF_COLS + lane, b = blockIdx.y;
+    const int HW = a.H * a.W;
+    const float* depth_b = a.depth + (long long)b * HW;
+    const float* mask_b = a.mask ? a.mask + (long long)b * HW : nullptr;
+    const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
+    const bool col_ok = x < a.W;
+    const int sx = col_ok ? a.col_fwd[x] : -1;
+    float m = INFINITY;
+    if (col_ok)
+        for (int ys = grp; ys < a.H; ys += UF_GROUPS) {
+            float zc;
+            band_weight(a, depth_b, mask_b, a.row_fwd[ys], __fdiv_rn(__fsub_rn((float)ys, cy), fy), sx, &zc);
+            m = (zc < m || zc != zc) ? zc : m;
+        }
+    m_s[grp][lane] = m;
+    __syncthreads();
+    if (grp == 0 && col_ok) {
+        for (int g = 1; g < UF_GROUPS; ++g) {
+            const float v = m_s[g][lane];
+            m = (m != m) ? m : ((v < m || v != v) ? v : m);
+        }
+        a.colmin[(long long)b * a.W + x] = m;
+    }
+}
 
 // Kernel 1: per-pixel weights, once.  One CTA = 32 columns x 32 rows of one item.  Every thread
 // evaluates both roles of a row index (as a shifted-frame row for the denominator, as an image row
@@ -78,12 +127,21 @@ __global__ void __launch_bounds__(UF_COLS * UF_GROUPS) ufield_weights_kernel(con
         yf_s[which][rr] = __fdiv_rn(__fsub_rn((float)ys, cy), fy);
     }
     __syncthreads();
+    const bool quash = a.quash > 0.f;
+    const float cmin_d = (quash && col_ok) ? a.colmin[(long long)b * a.W + x] : 0.f;
+    const float cmin_n = (quash && xi >= 0) ? a.colmin[(long long)b * a.W + xi] : 0.f;
     for (int rr = grp; rr < UF_ROWS; rr += UF_GROUPS) {
         const int r = r0 + rr;
         float wz = 0.f, w = 0.f;
         if (col_ok && r < a.H) {
-            wz = band_weight(a, depth_b, mask_b, sy_s[0][rr], yf_s[0][rr], sx_d);
-            if (yi_s[rr] >= 0 && xi >= 0) w = band_weight(a, depth_b, mask_b, sy_s[1][rr], yf_s[1][rr], sx_n);
+            if (quash) {
+                wz = quashed_weight(a, depth_b, mask_b, sy_s[0][rr], yf_s[0][rr], sx_d, cmin_d);
+                if (yi_s[rr] >= 0 && xi >= 0)
+                    w = quashed_weight(a, depth_b, mask_b, sy_s[1][rr], yf_s[1][rr], sx_n, cmin_n);
+            } else {
+                wz = band_weight(a, depth_b, mask_b, sy_s[0][rr], yf_s[0][rr], sx_d);
+                if (yi_s[rr] >= 0 && xi >= 0) w = band_weight(a, depth_b, mask_b, sy_s[1][rr], yf_s[1][rr], sx_n);
+            }
             const long long pix = (long long)b * HW + r * a.W + x;
             a.wmap[pix] = w;
             if (a.depth_zero != nullptr) a.depth_zero[pix] = __fmul_rn(__ldg(depth_b + r * a.W + x), w);
@@ -181,8 +239,8 @@ static int ufield_row_chunks(int H) { return (H + dpv::UF_ROWS - 1) / dpv::UF_RO
 
 extern "C" int64_t dpv_ufield_workspace_floats(int B, int D, int H, int W) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
-    // partial sums [B,chunks,D,W] + counts [B,chunks,W] + weight map [B,H,W]
-    return (int64_t)B * ufield_row_chunks(H) * (D + 1) * W + (int64_t)B * H * W;
+    // partial sums [B,chunks,D,W] + counts [B,chunks,W] + weight map [B,H,W] + column minima [B,W]
+    return (int64_t)B * ufield_row_chunks(H) * (D + 1) * W + (int64_t)B * H * W + (int64_t)B * W;
 }
 
 extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_candi,
@@ -190,9 +248,10 @@ extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_c
                           const int* row_inv, const int* col_fwd, const int* col_inv, float* uf,
                           float* depth_zero, float* workspace, int B, int D, int H, int W,
                           int64_t intr_bstride, int in_mode, float zstart, float zend, float maxd,
-                          float mind, float pad_depth, void* stream) {
+                          float mind, float pad_depth, float quash_range, void* stream) {
     using namespace dpv;
     DPV_CHECK_ARG(dpv && depth && d_candi && intr_up && row_fwd && row_inv && col_fwd && col_inv);
+    DPV_CHECK_ARG(quash_range >= 0.f);
     DPV_CHECK_ARG(uf && workspace);
     DPV_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0);
     DPV_CHECK_ARG(in_mode == DPV_IN_LOGPROB || in_mode == DPV_IN_PROB);
@@ -207,6 +266,8 @@ extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_c
     a.part = workspace;
     a.cnt = workspace + (long long)B * a.nchunk * D * W;
     a.wmap = a.cnt + (long long)B * a.nchunk * W;
+    a.colmin = a.wmap + (long long)B * H * W;
+    a.quash = quash_range;
     a.intr_bs = intr_bstride;
     a.zstart = zstart; a.zend = zend; a.maxd1 = maxd - 1.0f; a.mind = mind;
     a.pad_depth = pad_depth;
@@ -217,6 +278,11 @@ extern "C" int dpv_ufield(const float* dpv, const float* depth, const float* d_c
     const int nbg = (D + UF_GROUPS * DB - 1) / (UF_GROUPS * DB);
     if ((long long)B * nbg > 65535) return DPV_E_UNSUPP;
     dim3 grid0((W + UF_COLS - 1) / UF_COLS, a.nchunk, B), block(UF_COLS * UF_GROUPS);
+    if (quash_range > 0.f) {
+        dim3 gridm((W + UF_COLS - 1) / UF_COLS, B);
+        ufield_colmin_kernel<<<gridm, block, 0, st>>>(a);
+        DPV_LAUNCH_END();
+    }
     ufield_weights_kernel<<<grid0, block, 0, st>>>(a);
     DPV_LAUNCH_END();
     dim3 grid((W + UF_COLS - 1) / UF_COLS, a.nchunk, B * nbg);

@@ -130,7 +130,7 @@ class FrameStep:
         hk("ufield", 0)
         _lib.check(lib.dpv_ufield(p(self.refined), p(self.depth), p(self.d), p(intr_up), None,
                                   p(rf), p(ri), p(cf), p(ci), p(self.uf), p(self.dz), p(self.ws),
-                                  B, D, H, W, 9, ops.IN_LOGPROB, *self.uf_params, self.pad_depth, st))
+                                  B, D, H, W, 9, ops.IN_LOGPROB, *self.uf_params, self.pad_depth, 0.0, st))
         hk("ufield", 1)
 
     def capture(self, *args, **kw):

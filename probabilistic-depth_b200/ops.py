@@ -30,6 +30,12 @@ def _need(t, name, dtype=torch.float32):
         raise _lib.DpvError("%s must live on a CUDA device: the DPV kernels have no CPU path" % name)
     if t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.requires_grad and torch.is_grad_enabled():
+        # forward-only kernels: returning a detached result here would silently zero the gradients
+        # of whatever loss sits downstream (the reference's losses/losses.py:82-88 calls
+        # dpv_to_depthmap under grad)
+        raise _lib.DpvError("%s requires grad: the DPV kernels are forward-only (eval path); call them "
+                            "under torch.no_grad() or detach the input" % name)
     return t
 
 
@@ -53,18 +59,21 @@ def _per_item(t, B, shape, name):
     return t, int(np.prod(shape))
 
 
-_dcache = {}
-_dsum = {}
+_dcache = {}      # (bin bytes, device) -> fp32 device tensor, owned here, never modified
+_dsum = {}        # id(tensor owned by _dcache) -> fp32 sum of its bins
+_DCACHE_MAX = 64
 
 
 def _bin_sum(d):
-    """sum_k d_k in fp32: E[d] of an all-zero log-DPV column (exp(0) = 1 per bin)."""
-    key = (d.data_ptr(), d.numel(), str(d.device))
-    v = _dsum.get(key)
-    if v is None:
-        v = float(np.sum(d.detach().cpu().numpy(), dtype=np.float32))   # once per bin set
-        _dsum[key] = v
-    return v
+    """sum_k d_k in fp32: E[d] of an all-zero log-DPV column (exp(0) = 1 per bin).
+
+    Cached only for the tensors depth_bins() owns (alive and immutable for the life of the cache, so
+    id() identifies them).  A caller-supplied tensor may be freed, re-allocated at the same address or
+    changed in place, so its sum is taken from its content on every call (one 4*D-byte read-back)."""
+    v = _dsum.get(id(d))
+    if v is not None and _dcache.get(getattr(d, "_dpv_key", None)) is d:
+        return v
+    return float(np.sum(d.detach().cpu().numpy(), dtype=np.float32))
 
 
 def depth_bins(d_candi, device):
@@ -76,9 +85,13 @@ def depth_bins(d_candi, device):
     key = (arr.tobytes(), str(device))
     t = _dcache.get(key)
     if t is None:
+        if len(_dcache) >= _DCACHE_MAX:      # bounded: bin sets are a handful per process in practice
+            _dcache.clear()
+            _dsum.clear()
         t = torch.from_numpy(arr.astype(np.float32)).to(device)
+        t._dpv_key = key
         _dcache[key] = t
-        _dsum[(t.data_ptr(), t.numel(), str(t.device))] = float(np.sum(arr.astype(np.float32), dtype=np.float32))
+        _dsum[id(t)] = float(np.sum(arr.astype(np.float32), dtype=np.float32))
     return t
 
 
@@ -174,6 +187,9 @@ def head(x, d_candi, addend=None, mode="logits", logp=True, prob=False, depth=Fa
     B, D, H, W = x.shape
     if addend is not None:
         _need(addend, "addend")
+        if mode != "logits":
+            raise ValueError("addend is only defined for mode='logits' (log_softmax(x + addend), "
+                             "models/models.py:694)")
         if addend.shape != x.shape:
             raise ValueError("addend must match x")
         addend = addend.contiguous()
@@ -199,6 +215,13 @@ def head(x, d_candi, addend=None, mode="logits", logp=True, prob=False, depth=Fa
         _p(out.get("variance")), _p(out.get("argmax")), _p(out.get("quarter")),
         B, D, H, W, _MODE[mode], _stream()))
     return out
+
+
+def log_softmax(x):
+    """F.log_softmax(x, dim=1) over the bins of x [B,D,H,W] (reference models/models.py:351,560,637)."""
+    _need(x, "x")
+    D = x.shape[1]
+    return head(x, np.arange(D, dtype=np.float64), logp=True)["logp"]     # bin depths unused for logp alone
 
 
 # ----------------------------------------------------------------------------- K4c
@@ -304,7 +327,9 @@ def ufield(dpv, d_candi, intr_up, mode="logprob", mask=None, depth=None, params=
     """Uncertainty-field collapse, batched (reference utils/img_utils.py:268-358).
 
     dpv [B,D,H,W] in `mode` ("logprob" or "prob"); intr_up [B,3,3] or [3,3]; mask
-    [B,H,W] optional; depth [B,H,W] optional precomputed E[d].
+    [B,H,W] optional; depth [B,H,W] optional precomputed E[d].  params: pshift, zstart, zend,
+    maxd, mind (default: the KITTI constants) and optionally quash_range > 0 for the
+    quash_limit branch (:325-332; the reference's range is 1.0).
     Returns (uf [B,D,W], depth_zero [B,H,W]).
     """
     _need(dpv, "dpv")
@@ -329,7 +354,7 @@ def ufield(dpv, d_candi, intr_up, mode="logprob", mask=None, depth=None, params=
     _lib.check(lib.dpv_ufield(_p(dpv), _p(depth), _p(d), _p(intr_up), _p(mask), _p(rf), _p(ri),
                               _p(cf), _p(ci), _p(uf), _p(dz), _p(ws), B, D, H, W, i_bs, _MODE[mode],
                               f32(p["zstart"]), f32(p["zend"]), f32(p["maxd"]), f32(p["mind"]),
-                              pad_depth, _stream()))
+                              pad_depth, f32(p.get("quash_range", 0.0)), _stream()))
     return uf, dz
 
 
@@ -376,7 +401,8 @@ def head_ufield(x, d_candi, intr_up, mode="logits", logp=True, depth=True, varia
         raise ValueError("d_candi has %d bins, x has %d" % (d.numel(), D))
     lib = _lib.load()
     nws = int(lib.dpv_head_ufield_workspace_floats(B, D, H, W))
-    tabs = uf_fused_tables(H, W, p["pshift"], x.device) if (nws > 0 and W % 4 == 0) else None
+    quash = float(p.get("quash_range", 0.0)) > 0      # the column gate needs E[d] of the whole column first
+    tabs = uf_fused_tables(H, W, p["pshift"], x.device) if (nws > 0 and W % 4 == 0 and not quash) else None
     if tabs is None or mode == "prob":
         out = head(x, d, mode=mode, logp=True, depth=True, variance=variance, argmax=argmax,
                    quarter=quarter)

@@ -41,24 +41,26 @@ def gen_dpv_withmask(dmaps, masks, d_candi, var=0.3):
     return ops.lidar_prior(dmaps, masks, d_candi, var)
 
 
+QUASH_RANGE = 1.0      # utils/img_utils.py:326
+
+
 def _ufield_params(cfg, cfgx):
+    """utils/img_utils.py:269-290: the `cfgx` dict of the ROS caller (ros/ros_net.py:279) or the
+    dataset constants; quash_limit (:325-332) for cfgx and ILIM."""
     if cfgx is not None:
         zstart = cfgx["unc_shift"]
         return dict(pshift=cfgx["unc_ang"], zstart=zstart, zend=zstart + cfgx["unc_span"],
-                    maxd=100., mind=3.), True
+                    maxd=100., mind=3., quash_range=QUASH_RANGE)
     if "kitti" in cfg.data.dataset_path:
-        return dict(pshift=5, zstart=0.6, zend=0.6 + 0.3, maxd=100., mind=0.), False
+        return dict(pshift=5, zstart=0.6, zend=0.6 + 0.3, maxd=100., mind=0.)
     if "ilim" in cfg.data.dataset_path:
-        return dict(pshift=0, zstart=1.0, zend=1.0 + 0.3, maxd=100., mind=3.), True
+        return dict(pshift=0, zstart=1.0, zend=1.0 + 0.3, maxd=100., mind=3., quash_range=QUASH_RANGE)
     raise UnboundLocalError("gen_ufield: dataset_path names neither kitti nor ilim")
 
 
 def gen_ufield(dpv_predicted, d_candi, intr_up, visualizer=None, img=None, BV_log=True,
                normalize=False, mask=None, cfg=None, cfgx=None):
-    params, quash_limit = _ufield_params(cfg, cfgx)
-    if quash_limit:
-        raise NotImplementedError("gen_ufield: the quash_limit branch (ILIM / cfgx) is outside the "
-                                  "KITTI hot path and has no kernel yet")
+    params = _ufield_params(cfg, cfgx)
     if normalize:
         raise NotImplementedError("gen_ufield: normalize=True (visualisation only) has no kernel")
     if dpv_predicted.shape[0] != 1:

@@ -54,6 +54,42 @@ def sweep_case(name):
                 sigma=10.0, h=h, w=w)
 
 
+def sweep_wide_case(name):
+    """Round 2: images wider than 192 px, where dpv_sweep_cost_volume selects the exact-coordinate
+    (IEEE division) variant of the TMA kernel, up to the north-star's literal shape (features at 256x384,
+    C=67, D=64) and one 1280-wide large-D slab.  `sub` = (row start, row step, col start, col step) of the
+    part of the volume the golden file stores."""
+    spec = {
+        # name:             (h,   w,    C,  V, D,   pose kind, seed, sub)
+        "wide_48x256":      (48,  256,  19, 1, 32,  "mono",   71, (0, 1, 0, 1)),
+        "wide_stereo_24x320": (24, 320, 12, 1, 32,  "stereo", 72, (0, 1, 0, 1)),
+        "stress_256x384":   (256, 384,  67, 1, 64,  "mono",   73, (1, 4, 2, 4)),
+        "stress_stereo_256x384": (256, 384, 67, 1, 64, "stereo", 74, (2, 4, 1, 4)),
+        "large_d_96x1280":  (96,  1280, 8,  1, 128, "mono",   75, (0, 3, 5, 8)),
+    }[name]
+    h, w, C, V, D, kind, seed, sub = spec
+    K, rays = _cam(w, h)
+    d = synth.depth_candidates(5.0, 40.0, D, 1.0)
+    ref = synth.randn(seed, 1, C, h, w)
+    src = synth.randn(seed + 1000, 1, V, C, h, w)
+    if kind == "mono":
+        poses = [synth.pose(synth.yaw_matrix(0.7), (0.05, -0.02, 0.8))]
+    else:
+        poses = [synth.pose(None, (-0.54, 0.0, 0.0))]
+    P = np.stack(poses)
+    return dict(ref=ref, src=src, R=np.ascontiguousarray(P[:, :3, :3]),
+                t=np.ascontiguousarray(P[:, :3, 3]), K=K, rays=rays, d_candi=d,
+                sigma=10.0, h=h, w=w, sub=sub)
+
+
+def sub_view(vol, sub):
+    r0, rs, c0, cs = sub
+    return vol[..., r0::rs, c0::cs]
+
+
+SWEEP_WIDE_CASES = ["wide_48x256", "wide_stereo_24x320", "stress_256x384", "stress_stereo_256x384",
+                    "large_d_96x1280"]
+
 SWEEP_CASES = ["mono_small", "mono_yaw_2view", "stereo_small", "oob_heavy",
                "mono_ref_shape", "stereo_ref_shape", "odd_dims"]
 
@@ -132,6 +168,29 @@ def ufield_case(name):
 
 
 UFIELD_CASES = ["small_log", "full_log", "full_mask_lin", "odd_log"]
+
+
+def ufield_cfgx_case(name):
+    """Round 2: gen_ufield called with `cfgx` as ros/ros_net.py:279 does (utils/img_utils.py:269-275:
+    pshift = unc_ang, zstart = unc_shift, span = unc_span, mind = 3, quash_limit -> :325-332)."""
+    spec = {
+        # name            (H,   W,   seed, with_mask, log,  cfgx)
+        "ros_shift5":     (64,  96,  55, False, True,  dict(unc_ang=5, unc_shift=0.6, unc_span=0.3)),
+        "ros_noshift":    (128, 192, 56, False, True,  dict(unc_ang=0, unc_shift=0.55, unc_span=0.4)),
+        "ros_full_mask":  (256, 384, 57, True,  False, dict(unc_ang=3, unc_shift=0.6, unc_span=0.3)),
+        "ros_odd":        (37,  51,  58, False, True,  dict(unc_ang=2, unc_shift=0.5, unc_span=0.5)),
+    }[name]
+    H, W, seed, with_mask, log, cfgx = spec
+    K = synth.intrinsics(W // 4 if W % 4 == 0 else W, H // 4 if H % 4 == 0 else H)
+    Ku = synth.intrinsics_up(K) if (W % 4 == 0 and H % 4 == 0) else K
+    logits = synth.ground_plane_logits(seed, 1, H, W, D_CANDI, Ku)
+    mask = None
+    if with_mask:
+        mask = (synth.rng(seed + 1).uniform(size=(1, H, W)) < 0.7).astype(np.float32)
+    return dict(logits=logits, d_candi=D_CANDI, intr_up=Ku, mask=mask, log=log, cfgx=cfgx)
+
+
+UFIELD_CFGX_CASES = ["ros_shift5", "ros_noshift", "ros_full_mask", "ros_odd"]
 
 
 def corr_case(name):

@@ -12,7 +12,6 @@ its outputs are stored.  Inputs come from tests/golden/cases.py.
 """
 import os
 import sys
-import types
 import warnings
 
 import numpy as np
@@ -26,26 +25,13 @@ REF = os.environ.get("DPV_REFERENCE", "/root/reference")
 
 
 def import_reference():
-    sys.path.insert(0, REF)
-    import external.deval_lib as _dl
-    stub = types.ModuleType("external.deval_lib.pyevaluatedepth_lib")
-    stub.evaluateErrors = lambda e: {}
-    stub.depthError = lambda a, b: [0.0] * 9
-    sys.modules[stub.__name__] = stub
-    _dl.pyevaluatedepth_lib = stub
-    _rep = torch.Tensor.repeat
-
-    def _repeat(self, *a):
-        if a and isinstance(a[0], (list, tuple)):
-            a = (a[0],)
-        return _rep(self, *a)
-    torch.Tensor.repeat = _repeat
-    if not torch.cuda.is_available():
-        torch.nn.Module.cuda = lambda s, *a, **k: s
-    import warping.homography as homography
-    import utils.img_utils as img_utils
-    import models.correlation_native as correlation_native
-    return homography, img_utils, correlation_native
+    """(homography, img_utils, correlation_native) of the unmodified reference; the shims live in
+    oracle/reference_loader.py (shared with the GPU-side second-oracle tests)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import reference_loader
+    os.environ.setdefault("DPV_REFERENCE", REF)
+    ref = reference_loader.load()
+    return ref.homography, ref.img_utils, ref.correlation_native
 
 
 class _Cfg:

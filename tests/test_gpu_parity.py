@@ -19,6 +19,7 @@ import torch
 
 import cases
 from oracle import dpv_oracle as O
+from uf_helpers import near_threshold_columns
 
 pytestmark = pytest.mark.gpu
 T = torch.from_numpy
@@ -70,6 +71,23 @@ def test_sweep_vs_golden(dpv, golden, name, dist, algo):
     got = dpv.ops.sweep_cost_volume(cu(c["ref"]), cu(c["src"]), cu(poses), cu(c["K"]), cu(c["rays"]),
                                     c["d_candi"], c["sigma"], dist=dist, algo=algo)
     close(got, want)
+
+
+@pytest.mark.parametrize("name", cases.SWEEP_WIDE_CASES)
+@pytest.mark.parametrize("algo", [0, 4, 1])
+def test_sweep_wide_vs_golden(dpv, golden, name, algo):
+    """Images wider than 192 px -- the exact-coordinate variant of the TMA kernel
+    (sweep_gram_tma_kernel<.,EXACT>) -- against the reference's own outputs, up to the north-star's
+    literal shape (features at 256x384, C=67, D=64) and a 1280-wide, D=128 slab."""
+    c = cases.sweep_wide_case(name)
+    V = c["src"].shape[1]
+    poses = np.zeros((1, V, 4, 4), np.float32)
+    poses[0, :, :3, :3] = c["R"]
+    poses[0, :, :3, 3] = c["t"]
+    poses[0, :, 3, 3] = 1
+    got = dpv.ops.sweep_cost_volume(cu(c["ref"]), cu(c["src"]), cu(poses), cu(c["K"]), cu(c["rays"]),
+                                    c["d_candi"], c["sigma"], dist="L2", algo=algo)
+    close(cases.sub_view(got, c["sub"]), golden("sweep_wide")[name + "_L2"])
 
 
 @pytest.mark.parametrize("name", ["mono_small", "mono_yaw_2view", "oob_heavy"])
@@ -262,22 +280,10 @@ def test_fusion(dpv, golden, name):
 
 
 # ------------------------------------------------------------------------- K5
-def _near_threshold_columns(c, log):
+def _near_threshold_columns(c, log, params=None):
     """Columns holding a pixel whose height/depth is within 1e-4 (relative) of a mask threshold."""
     ls = O.log_softmax_bins(T(c["logits"]))
-    dpvv = ls if log else torch.exp(ls)
-    H, W = dpvv.shape[2:]
-    g_fwd, _ = O._shift_grids(H, W, 5)
-    shifted = torch.nn.functional.grid_sample(dpvv, g_fwd, mode="nearest", align_corners=False)
-    z = O.expected_depth(shifted, c["d_candi"], log=log)
-    pts = O.depth_to_points(z, T(c["intr_up"]))
-    bad = torch.zeros((H, W), dtype=torch.bool)
-    for val, thr in ((pts[1], 0.9), (pts[1], 0.6), (pts[2], 99.0), (pts[2], 0.0)):
-        gap = (val - thr).abs()
-        bad |= (gap > 0) & (gap <= 1e-4 * max(1.0, abs(thr)))   # exact hits (zero padding) are not rounding-sensitive
-    cols = bad.any(0)
-    # the mask is shifted back up by 5 rows and keeps its column: same column index
-    return cols.numpy()
+    return near_threshold_columns(ls if log else torch.exp(ls), c["d_candi"], T(c["intr_up"]), log, params)
 
 
 @pytest.mark.parametrize("name", cases.UFIELD_CASES)
@@ -299,6 +305,31 @@ def test_ufield(dpv, golden, name):
     np.testing.assert_array_equal(np.isnan(uf[:, :, keep]), np.isnan(want_uf[:, :, keep]))
     np.testing.assert_allclose(uf[:, :, keep], want_uf[:, :, keep], rtol=1e-4, atol=1e-7, equal_nan=True)
     np.testing.assert_allclose(dz.cpu().numpy()[:, :, keep], want_dz[:, :, keep], rtol=1e-4, atol=0)
+
+
+@pytest.mark.parametrize("name", cases.UFIELD_CFGX_CASES)
+def test_ufield_cfgx_quash_limit(dpv, golden, name):
+    """gen_ufield(..., cfgx=...) as ros/ros_net.py:279 calls it: quash_limit branch
+    (utils/img_utils.py:269-275,325-332), with and without a row shift / GT mask / linear input."""
+    g = golden("ufield_cfgx")
+    c = cases.ufield_cfgx_case(name)
+    ls = dpv.ops.head(cu(c["logits"]), c["d_candi"], logp=True)["logp"]
+    vol = ls if c["log"] else torch.exp(ls)
+    uf, dz = dpv.utils.img_utils.gen_ufield(vol, c["d_candi"], cu(c["intr_up"]), BV_log=c["log"],
+                                            mask=cu(c["mask"]), cfgx=c["cfgx"])
+    want_uf, want_dz = g[name + "_uf"], g[name + "_depthzero"]
+    keep = ~_near_threshold_columns(c, c["log"], O.cfgx_params(c["cfgx"]))
+    assert keep.mean() > 0.9
+    uf = uf.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(uf[:, :, keep]), np.isnan(want_uf[:, :, keep]))
+    np.testing.assert_allclose(uf[:, :, keep], want_uf[:, :, keep], rtol=1e-4, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(dz.cpu().numpy()[:, :, keep], want_dz[:, :, keep], rtol=1e-4, atol=0)
+    # the fused entry point takes the same branch through its two-kernel form
+    if c["log"] and c["mask"] is None:
+        p = dict(dpv.utils.img_utils._ufield_params(None, c["cfgx"]))
+        out = dpv.ops.head_ufield(cu(c["logits"]), c["d_candi"], cu(c["intr_up"]), params=p)
+        np.testing.assert_allclose(out["uf"].cpu().numpy()[:, :, keep], want_uf[:, :, keep], rtol=1e-4,
+                                   atol=1e-7, equal_nan=True)
 
 
 @pytest.mark.parametrize("name", ["small_log", "full_log"])

@@ -29,7 +29,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol(dpv):
     for n in names:
         assert hasattr(lib, n), "libdpv_sm100a.so does not export %s" % n
     assert sorted(dpv._lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
-    assert dpv._lib.load().dpv_abi_version() == 1
+    assert dpv._lib.load().dpv_abi_version() == 2
     assert dpv._lib.load().dpv_error_string(-1).decode().startswith("dpv: bad argument")
 
 

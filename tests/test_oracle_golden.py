@@ -35,6 +35,16 @@ def test_sweep(golden, name, dist):
     _close(cv.numpy(), g[key], rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("name", cases.SWEEP_WIDE_CASES)
+def test_sweep_wide(golden, name):
+    """Images wider than 192 px up to the north-star's literal 256x384 / C=67 / D=64 shape and a
+    1280-wide large-D slab (round-2 goldens, tests/golden/make_golden_r2.py)."""
+    c = cases.sweep_wide_case(name)
+    cv = O.plane_sweep_cost(T(c["ref"]), T(c["src"]), c["d_candi"], T(c["R"]), T(c["t"]),
+                            T(c["K"]), T(c["rays"]), c["sigma"], "L2")
+    _close(cases.sub_view(cv.numpy(), c["sub"]), golden("sweep_wide")[name + "_L2"], rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("name", cases.WARP_FEATURE_CASES)
 def test_warp_feature(golden, name):
     c = cases.warp_feature_case(name)
@@ -89,6 +99,25 @@ def test_ufield(golden, name):
     np.testing.assert_array_equal(uf.numpy(), g[name + "_uf"])
     np.testing.assert_array_equal(dz.numpy(), g[name + "_depthzero"])
     assert np.isfinite(g[name + "_uf"]).any(), "mask selects nothing: vacuous case"
+
+
+@pytest.mark.parametrize("name", cases.UFIELD_CFGX_CASES)
+def test_ufield_cfgx_quash_limit(golden, name):
+    """gen_ufield as the ROS caller invokes it (cfgx -> quash_limit, utils/img_utils.py:269-275,325-332)."""
+    g = golden("ufield_cfgx")
+    c = cases.ufield_cfgx_case(name)
+    ls = O.log_softmax_bins(T(c["logits"]))
+    dpv = ls if c["log"] else torch.exp(ls)
+    mask = None if c["mask"] is None else T(c["mask"])
+    uf, dz = O.uncertainty_field(dpv, c["d_candi"], T(c["intr_up"]), log=c["log"], mask=mask,
+                                 params=O.cfgx_params(c["cfgx"]))
+    np.testing.assert_array_equal(uf.numpy(), g[name + "_uf"])
+    np.testing.assert_array_equal(dz.numpy(), g[name + "_depthzero"])
+    assert np.isfinite(g[name + "_uf"]).any(), "mask selects nothing: vacuous case"
+    # the gate does something: without it the field differs
+    uf0, _ = O.uncertainty_field(dpv, c["d_candi"], T(c["intr_up"]), log=c["log"], mask=mask,
+                                 params=dict(O.cfgx_params(c["cfgx"]), quash_limit=False))
+    assert not np.array_equal(np.nan_to_num(uf0.numpy()), np.nan_to_num(uf.numpy()))
 
 
 @pytest.mark.parametrize("name", cases.CORR_CASES)

@@ -1,0 +1,300 @@
+"""The second oracle of SURVEY.md 8c: the UNMODIFIED reference running on cuda:0 through torch.
+
+Same weights, same cuDNN convolutions (TF32 off), same inputs -- only the hot path differs:
+  (R) reference BaseModel, untouched                      (models/models.py:440-710)
+  (P) the same reference object after dpv.patch_reference(): its own forward code, hot-path
+      functions swapped for the sm_100a kernels
+  (M) our mirror BaseModel with the reference's weights loaded (batched launches)
+Bar (BASELINE.json north_star): log-DPV, E[d], Var within 1e-4 relative; arg-max indices identical
+except where the reference's own top-2 margin is inside that noise (count and margin are printed and
+written to gpurun_out/model_parity.json).
+
+The reference tree is found by oracle/reference_loader.py: /root/reference in the build container,
+the git-ignored copy baseline/_ref (made by __graft_entry__.build()) on the GPU box.
+"""
+import importlib
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import model_cases as MC  # noqa: E402
+from oracle import reference_frame, reference_loader  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not reference_loader.available(),
+                                 reason="no reference tree (run __graft_entry__.build() where /root/reference exists)")]
+
+TOL = 1e-4
+REPORT = {}
+
+
+@pytest.fixture(scope="module")
+def ref():
+    warnings.filterwarnings("ignore")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    r = reference_loader.load()
+    yield r
+    reference_loader.restore()
+    os.makedirs(os.path.join(os.path.dirname(HERE), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(HERE), "gpurun_out", "model_parity.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def scaled(a, b):
+    """max |a - b| / max(1, |b|)  (the log-DPV rule; for E[d] >= 5 and Var it is the relative error)."""
+    a, b = a.double(), b.double()
+    return float(((a - b).abs() / b.abs().clamp_min(1.0)).max())
+
+
+def moments(logdpv, d_candi):
+    """E[d] and Var exactly as the trainer forms them, in float64 (trainer/default_trainer.py:333-336)."""
+    dd = torch.tensor(d_candi, device=logdpv.device).reshape(1, -1, 1, 1)
+    z = torch.exp(logdpv.double())
+    mean = torch.sum(dd * z, dim=1)
+    return mean, torch.sum(((dd.expand_as(z) - mean.unsqueeze(1)) ** 2) * z, dim=1)
+
+
+def compare(tag, got, want, d_candi):
+    """got / want: log-DPV [B,D,H,W] of ours / of the reference.  Returns the report entry."""
+    e_log = scaled(got, want)
+    mg, vg = moments(got, d_candi)
+    mw, vw = moments(want, d_candi)
+    e_mean = float(((mg - mw).abs() / mw.abs()).max())
+    e_var = float(((vg - vw).abs() / vw.abs().clamp_min(1e-3)).max())
+    ag, aw = torch.argmax(got, 1), torch.argmax(want, 1)
+    flips = ag != aw
+    top2 = torch.topk(want, 2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    entry = {"log_dpv": e_log, "mean": e_mean, "var": e_var, "argmax_flips": int(flips.sum()),
+             "pixels": int(flips.numel()),
+             "max_top2_margin_at_flips": float(margin[flips].max()) if flips.any() else 0.0,
+             "min_top2_margin": float(margin.min())}
+    REPORT[tag] = entry
+    print(tag, entry)
+    return entry
+
+
+def check(entry, tol=TOL):
+    assert entry["log_dpv"] <= tol, entry
+    assert entry["mean"] <= tol, entry
+    assert entry["var"] <= tol, entry
+    # an arg-max may only move where the reference's own top-2 margin is inside the tolerance
+    assert entry["max_top2_margin_at_flips"] <= 2 * tol, entry
+
+
+def ref_model(ref, name):
+    torch.manual_seed(0)
+    return MC.batch_stat_norm(ref.models.BaseModel(MC.cfg(name), 0)).cuda()
+
+
+def mirror_model(name, like):
+    OM = importlib.import_module("probabilistic-depth_b200.models.models")
+    torch.manual_seed(0)
+    m = OM.BaseModel(MC.cfg(name), 0)
+    m.load_state_dict(like.state_dict())            # zip-by-position contract: same keys, same order
+    if hasattr(like, "based_3d"):                   # the unregistered residual blocks (models/models.py:394-399)
+        for a, b in zip(m.based_3d.dres_modules, like.based_3d.dres_modules):
+            a.load_state_dict(b.state_dict())
+    return MC.batch_stat_norm(m).cuda()
+
+
+def inputs(name, frame, batch):
+    mi = MC.frame_inputs(name, frame, batch)
+    return {k: (cu(v) if isinstance(v, np.ndarray) and k != "d_candi" else v) for k, v in mi.items()}
+
+
+def outputs_of(res, nmode):
+    bv = res["output"][0] if nmode == "default_upsample" else res["output"][-1]
+    return bv, res["output_refined"][-1]
+
+
+def handoff(refined):
+    return torch.nn.functional.interpolate(refined, scale_factor=0.25, mode="nearest")   # default_trainer.py:221-222
+
+
+def run_chain(model, name, frames, batch, prevs=None):
+    """Frames chained through prev_output as the trainer does; `prevs` (a list) teacher-forces the
+    hand-off with another run's."""
+    nmode = MC.MODES[name][0]
+    outs, prev = [], None
+    for f in range(frames):
+        t = inputs(name, f, batch)
+        t["prev_output"] = prev if prevs is None else prevs[f]
+        with torch.no_grad():
+            res = model([t])[0]
+        bv, refined = outputs_of(res, nmode)
+        outs.append((bv, refined))
+        prev = handoff(refined)
+    return outs
+
+
+@pytest.mark.parametrize("name,batch", [("default_stereo", 2), ("upsample_mono", 2)])
+def test_basemodel_reference_vs_patched_vs_mirror(dpv, ref, name, batch):
+    model = ref_model(ref, name)
+    want = run_chain(model, name, 1, batch)
+    launches0 = dpv._lib.launch_count()
+    dpv.patch_reference(ref.homography, ref.img_utils, ref.models)
+    try:
+        assert ref.homography.est_swp_volume_v4.__module__.startswith("probabilistic-depth_b200")
+        patched = run_chain(model, name, 1, batch)
+    finally:
+        reference_loader.restore()
+    assert ref.homography.est_swp_volume_v4.__module__ == "warping.homography"
+    # per item: one sweep launch, two log-softmax sites, (upsample) the prior
+    assert dpv._lib.launch_count() - launches0 >= 3 * batch
+    mirror = run_chain(mirror_model(name, model), name, 1, batch)
+    for tag, got in (("patched", patched), ("mirror", mirror)):
+        check(compare("%s/%s/bv" % (name, tag), got[0][0], want[0][0], MC.D_CANDI))
+        check(compare("%s/%s/refined" % (name, tag), got[0][1], want[0][1], MC.D_CANDI))
+
+
+def test_feedback_16_frames_reference_vs_patched_vs_mirror(dpv, ref):
+    """default_feedback, 16 chained frames (BASELINE.json configs[2]).  Teacher-forced: every arm gets the
+    reference's own hand-off, so each frame is a like-for-like comparison at 1e-4.  Free-running: each arm
+    chains its own outputs; the drift after 16 frames is reported and bounded."""
+    name, frames = "feedback_mono", 16
+    model = ref_model(ref, name)
+    want = run_chain(model, name, frames, 1)
+    prevs = [None] + [handoff(r) for _, r in want[:-1]]
+    dpv.patch_reference(ref.homography, ref.img_utils, ref.models)
+    try:
+        forced = run_chain(model, name, frames, 1, prevs)
+        free = run_chain(model, name, frames, 1)
+    finally:
+        reference_loader.restore()
+    mir = mirror_model(name, model)
+    m_forced = run_chain(mir, name, frames, 1, prevs)
+    m_free = run_chain(mir, name, frames, 1)
+    worst = {}
+    for tag, got in (("patched_forced", forced), ("mirror_forced", m_forced), ("patched_free", free),
+                     ("mirror_free", m_free)):
+        es = [compare("%s/%s/f%02d" % (name, tag, f), got[f][1], want[f][1], MC.D_CANDI) for f in range(frames)]
+        eb = [scaled(got[f][0], want[f][0]) for f in range(frames)]
+        worst[tag] = {k: max(e[k] for e in es) for k in ("log_dpv", "mean", "var", "max_top2_margin_at_flips")}
+        worst[tag]["bv_upd"] = max(eb)
+        worst[tag]["argmax_flips"] = sum(e["argmax_flips"] for e in es)
+    REPORT[name + "/worst"] = worst
+    print(json.dumps(worst, indent=1))
+    for tag in ("patched_forced", "mirror_forced"):
+        w = worst[tag]
+        assert w["log_dpv"] <= TOL and w["mean"] <= TOL and w["var"] <= TOL and w["bv_upd"] <= TOL, (tag, w)
+        assert w["max_top2_margin_at_flips"] <= 2 * TOL, (tag, w)
+    for tag in ("patched_free", "mirror_free"):      # 16 frames of compounding through the 3-D net
+        assert worst[tag]["log_dpv"] <= 10 * TOL, (tag, worst[tag])
+
+
+# ---------------------------------------------------------------------------- function level
+def test_hot_path_functions_reference_on_cuda_vs_ours(dpv, ref):
+    """Each reference function of SURVEY.md 8a on cuda:0 (torch-CUDA grid_sample / softmax, whose fp32
+    contraction differs from the CPU's) against our kernel on the same device tensors, model shapes."""
+    s = dpv.synth
+    D, h, w, H, W, C = 64, 64, 96, 256, 384, 67
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(w, h, 1)
+    K, rays = cu(cam["intrinsics"][0]), cu(cam["unit_ray"][0])
+    camd = {"intrinsic_M_cuda": K, "intrinsic_M": cam["intrinsics"][0], "unit_ray_array_2D": rays}
+    feats = cu(s.randn(11, 1, 2, C, h, w))
+    for kind, pose in (("mono", s.mono_poses(1)), ("stereo", s.stereo_poses(1))):
+        P = cu(pose.astype(np.float32))
+        R, t = P[0, :-1, :3, :3], P[0, :-1, :3, 3]
+        want = ref.homography.est_swp_volume_v4(feats[:, -1], feats[:, :-1], d, R, t, camd, 10.0, feat_dist="L2")
+        got = dpv.warping.homography.est_swp_volume_v4(feats[:, -1], feats[:, :-1], d, R, t, camd, 10.0,
+                                                       feat_dist="L2")
+        e = float(((got - want).abs() / want.abs().clamp_min(1e-1)).max())
+        REPORT["fn/est_swp_volume_v4/" + kind] = e
+        assert e <= TOL, (kind, e)
+    raw = cu(s.randn(12, 1, 2, D, h, w))
+    P = cu(s.mono_poses(1).astype(np.float32))
+    want = ref.homography.warp_feature(raw, d, P[0, :, :3, :3], P[0, :, :3, 3], camd)
+    got = dpv.warping.homography.warp_feature(raw, d, P[0, :, :3, :3], P[0, :, :3, 3], camd)
+    REPORT["fn/warp_feature"] = float((got - want).abs().max())
+    assert float((got - want).abs().max()) <= TOL
+    # K4c
+    dm, mk = s.sparse_depth(13, 2, h, w)
+    want = ref.img_utils.gen_dpv_withmask(cu(dm), cu(mk), d, 0.3)
+    got = dpv.utils.img_utils.gen_dpv_withmask(cu(dm), cu(mk), d, 0.3)
+    REPORT["fn/gen_dpv_withmask"] = float(((got - want).abs() / want).max())
+    assert REPORT["fn/gen_dpv_withmask"] <= TOL
+    # K3 + K5 at full resolution
+    Ku = cu(cam["intrinsics_up"][0])
+    logits = cu(s.ground_plane_logits(14, 1, H, W, d, cam["intrinsics_up"][0]))
+    want_ls = torch.nn.functional.log_softmax(logits, dim=1)
+    got_ls = dpv.ops.log_softmax(logits)
+    assert scaled(got_ls, want_ls) <= TOL
+    want_d = ref.img_utils.dpv_to_depthmap(want_ls, d, BV_log=True)
+    got_d = dpv.utils.img_utils.dpv_to_depthmap(want_ls, d, BV_log=True)
+    assert float(((got_d - want_d).abs() / want_d).max()) <= TOL
+    from uf_helpers import near_threshold_columns
+    for tag, kw, params in (("kitti", dict(cfg=reference_loader.KittiCfg), None),
+                            ("cfgx", dict(cfgx=dict(unc_ang=5, unc_shift=0.6, unc_span=0.3)),
+                             dict(pshift=5, zstart=0.6, zend=0.6 + 0.3, maxd=100., mind=3., quash_limit=True))):
+        want_uf, want_dz = ref.img_utils.gen_ufield(want_ls, d, Ku, BV_log=True, **kw)
+        got_uf, got_dz = dpv.utils.img_utils.gen_ufield(want_ls, d, Ku, BV_log=True, **kw)
+        keep = torch.from_numpy(~near_threshold_columns(want_ls.cpu(), d, Ku.cpu(), True, params)).cuda()
+        assert float(keep.float().mean()) > 0.9
+        a, b = got_uf[:, :, keep], want_uf[:, :, keep]
+        assert torch.equal(torch.isnan(a), torch.isnan(b)), tag
+        fin = torch.isfinite(b)
+        e = float(((a[fin] - b[fin]).abs() / b[fin].abs().clamp_min(1e-6)).max())
+        REPORT["fn/gen_ufield/" + tag] = e
+        assert e <= TOL, (tag, e)
+        assert float((got_dz - want_dz).abs()[:, :, keep].max()) <= 1e-4 * 40
+
+
+def test_frame_step_vs_reference_on_cuda_bench_shape(dpv, ref):
+    """The bench step itself (B=8, D=64, 256x384, C=67) against the reference's functions run on the same
+    device tensors -- a size the CPU oracle does not reach in test time."""
+    frame = importlib.import_module("probabilistic-depth_b200.frame")
+    from uf_helpers import near_threshold_columns
+    s = dpv.synth
+    B, V, C, D, h, w, H, W = 8, 1, 67, 64, 64, 96, 256, 384
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(w, h, B)
+    feats, poses = cu(s.randn(21, B, V + 1, C, h, w)), cu(s.stereo_poses(B).astype(np.float32))
+    K, rays, Ku = cu(cam["intrinsics"]), cu(cam["unit_ray"]), cu(cam["intrinsics_up"])
+    logits = cu(s.ground_plane_logits(22, B, H, W, d, cam["intrinsics_up"][0]))
+    step = frame.FrameStep(B, V, C, D, h, w, H, W, d)
+    step.run(feats, poses, K, rays, logits, Ku)
+    want = reference_frame.frame_hot_path(ref, feats, poses, K, rays, d, 10.0, logits, Ku)
+    torch.cuda.synchronize()
+    errs = {"cost": float(((step.cost - want["cost"]).abs() / want["cost"].abs().clamp_min(1e-1)).max()),
+            "bv": scaled(step.bv, want["bv"]), "refined": scaled(step.refined, want["refined"]),
+            "depth": float(((step.depth - want["depth"]).abs() / want["depth"]).max()),
+            "var": float(((step.var.double() - want["var"]).abs() / want["var"].clamp_min(1e-3)).max())}
+    REPORT["frame_step_b8"] = errs
+    print(errs)
+    assert all(v <= TOL for v in errs.values()), errs
+    flips = step.argmax != want["argmax"]
+    top2 = torch.topk(want["refined"], 2, dim=1).values
+    assert not flips.any() or float((top2[:, 0] - top2[:, 1])[flips].max()) <= 2 * TOL
+    assert torch.equal(step.quarter, want["quarter"]) or scaled(step.quarter, want["quarter"]) <= TOL
+    for b in range(B):
+        keep = torch.from_numpy(~near_threshold_columns(want["refined"][b:b + 1].cpu(), d, Ku[b].cpu(), True)).cuda()
+        assert float(keep.float().mean()) > 0.9
+        a, c = step.uf[b:b + 1][:, :, keep], want["uf"][b:b + 1][:, :, keep]
+        assert torch.equal(torch.isnan(a), torch.isnan(c))
+        fin = torch.isfinite(c)
+        assert float(((a[fin] - c[fin]).abs() / c[fin].abs().clamp_min(1e-6)).max()) <= TOL
+
+
+def test_patched_ops_refuse_autograd(dpv, ref):
+    """The kernels are forward-only: under grad they raise instead of returning detached tensors
+    (the reference's loss calls dpv_to_depthmap under grad, losses/losses.py:82-88)."""
+    x = torch.randn(1, 64, 8, 12, device="cuda", requires_grad=True)
+    with pytest.raises(dpv.DpvError, match="forward-only"):
+        dpv.utils.img_utils.dpv_to_depthmap(torch.log_softmax(x, 1), MC.D_CANDI, BV_log=True)
+    with torch.no_grad():
+        dpv.utils.img_utils.dpv_to_depthmap(torch.log_softmax(x, 1), MC.D_CANDI, BV_log=True)
