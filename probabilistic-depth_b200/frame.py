@@ -156,8 +156,11 @@ class FrameStep:
             n -= 1
         return n - 2 if self.fused_uf else n
 
-    # -- algorithmic bytes, per step ---------------------------------
-    def algorithmic_bytes(self):
+    # -- bytes per step --------------------------------------------------------------------
+    def survey_bytes(self):
+        """SURVEY.md section 8d accounting: every kernel of the reference's decomposition as its own pass
+        (K5 re-reads the DPV, the 1/4-res soft-max is a separate read + write).  This is the numerator the
+        survey's 60 % target is defined on; it is NOT what this step moves when passes are fused."""
         B, V, C, D = self.B, self.V, self.C, self.D
         hw, HW = self.h * self.w, self.H * self.W
         k = {
@@ -166,6 +169,30 @@ class FrameStep:
             "head_full": 8 * HW * D + 16 * HW,
             "ufield": 4 * HW * D + 4 * D * self.W + 8 * HW,
         }
+        if self.mode == "upsample":
+            k["bayes_fuse"] = 12 * hw * D + 8 * hw
+        if self.mode == "feedback":
+            k["warp_feature"] = 8 * hw * D * (V + 1) + 12 * hw
+            k["feedback_fuse"] = 12 * hw * D
+        return {n: v * B for n, v in k.items()}
+
+    def algorithmic_bytes(self):
+        """Bytes of the LAUNCHED configuration: each kernel's inputs read once and outputs written once.
+        A pass that was fused away is not counted: with the 1/4-res log-softmax in the sweep epilogue the
+        sweep additionally writes the log-DPV (4 hw D) and `head_quarter` disappears; with the fused head +
+        UF the DPV is not re-read, the fused kernel additionally writes UF [D,W] and depth_zero [H,W]."""
+        B, V, C, D = self.B, self.V, self.C, self.D
+        hw, HW = self.h * self.w, self.H * self.W
+        k = {"sweep": 4 * hw * (C * (1 + V) + D) + 12 * hw}
+        if self.fuse_lsm:
+            k["sweep"] += 4 * hw * D
+        else:
+            k["head_quarter"] = 8 * hw * D
+        if self.fused_uf:
+            k["head_full_ufield"] = 8 * HW * D + 16 * HW + 4 * D * self.W + 4 * HW
+        else:
+            k["head_full"] = 8 * HW * D + 16 * HW
+            k["ufield"] = 4 * HW * D + 4 * D * self.W + 8 * HW
         if self.mode == "upsample":
             k["bayes_fuse"] = 12 * hw * D + 8 * hw
         if self.mode == "feedback":
