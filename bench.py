@@ -373,8 +373,7 @@ def run_ours(args, dpv):
                          "note": ("fused K3+K5: bytes of the fused operation itself (logits in, log-DPV and the "
                                   "per-pixel / per-column products out); SURVEY 8d counts K5 as a second pass "
                                   "over the DPV, see unfused_bytes_frac") if step.fused_uf else "K3 alone",
-                         "unfused_bytes_frac": ((alg["head_full"] + alg["ufield"]) / (head_mean_ms * 1e-3) / 1e9 / peak)
-                         if step.fused_uf else None},
+                         "unfused_bytes_frac": None},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "dpv_pipeline_run (host buffers, pinned)"},

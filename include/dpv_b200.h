@@ -68,7 +68,14 @@ long long dpv_launch_count(void);
  * algo  : 0 = choose, 1 = direct per-plane gather (L1 or L2), 2 = per-cell Gram form with global
  *         gathers (L2), 3 = per-cell Gram form staged through shared memory with cp.async (L2),
  *         4 = per-cell Gram form, TMA-fed, four lanes per pixel (L2, production path; needs W % 4 == 0
- *         and 16-byte aligned ref/src bases and strides -- "choose" falls back to 3/2 otherwise).
+ *         and 16-byte aligned ref/src bases and strides -- "choose" falls back to 3/2 otherwise),
+ *         5 = cross-correlation form (L2; dpv_sweep_cost_volume_ws only): the products between source
+ *         pixels are taken once per call by a pre-pass into `workspace`, the tile kernel computes one
+ *         banded correlation <ref pixel, source pixel> per tap; same shape conditions as 4.  "choose"
+ *         takes 5 whenever a workspace is given.
+ * dpv_sweep_cost_volume_ws: the same call with a caller-owned scratch buffer of
+ *         dpv_sweep_workspace_floats(B, V, H, W) floats (16-byte aligned, contents irrelevant before and
+ *         after the call, not shared by calls that run concurrently); dpv_sweep_cost_volume == workspace NULL.
  */
 int dpv_sweep_cost_volume(const float* ref, const float* src, const float* pose, const float* K,
                           const float* rays, const float* d_candi, float* cost,
@@ -77,6 +84,14 @@ int dpv_sweep_cost_volume(const float* ref, const float* src, const float* pose,
                           int64_t ref_bstride, int64_t src_bstride, int64_t src_vstride,
                           int64_t pose_bstride, int64_t k_bstride, int64_t rays_bstride,
                           float sigma, int dist, int algo, void* stream);
+int64_t dpv_sweep_workspace_floats(int B, int V, int H, int W);
+int dpv_sweep_cost_volume_ws(const float* ref, const float* src, const float* pose, const float* K,
+                             const float* rays, const float* d_candi, float* cost,
+                             float* log_softmax_out,
+                             int B, int V, int C, int D, int H, int W,
+                             int64_t ref_bstride, int64_t src_bstride, int64_t src_vstride,
+                             int64_t pose_bstride, int64_t k_bstride, int64_t rays_bstride,
+                             float sigma, int dist, int algo, float* workspace, void* stream);
 
 /* ---- K1 stand-alone : per-plane warp ----------------------------------------------------
  * Replaces _back_warp_homo_parallel (warping/homography.py:170-198) for callers that want

@@ -21,6 +21,8 @@ PROTOTYPES = {
     "dpv_error_string": (ctypes.c_char_p, [_c_i]),
     "dpv_launch_count": (ctypes.c_longlong, []),
     "dpv_sweep_cost_volume": (_c_i, [_c_fp] * 8 + [_c_i] * 6 + [_c_i64] * 6 + [_c_f, _c_i, _c_i, _c_fp]),
+    "dpv_sweep_workspace_floats": (_c_i64, [_c_i] * 4),
+    "dpv_sweep_cost_volume_ws": (_c_i, [_c_fp] * 8 + [_c_i] * 6 + [_c_i64] * 6 + [_c_f, _c_i, _c_i, _c_fp, _c_fp]),
     "dpv_warp_planes": (_c_i, [_c_fp] * 5 + [_c_i] * 4 + [_c_i64, _c_f, _c_f, _c_fp]),
     "dpv_warp_feature": (_c_i, [_c_fp] * 6 + [_c_i] * 5 + [_c_i64] * 3 + [_c_fp]),
     "dpv_head": (_c_i, [_c_fp] * 9 + [_c_i] * 5 + [_c_fp]),

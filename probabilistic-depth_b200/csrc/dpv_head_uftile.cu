@@ -26,6 +26,7 @@ namespace dpv {
 
 constexpr int UT_NT = 128, UT_NW = 4;
 constexpr int UT_ROWS = 8;            // rows per tile (two per warp)
+constexpr int UT_MAXCH = 1024;        // tiles per column strip (H <= 8192)
 constexpr float kUtL2e = 1.4426950408889634f;
 constexpr float kUtLn2 = 0.6931471805599453f;
 
@@ -122,6 +123,18 @@ __global__ void __launch_bounds__(UT_NT, 5) head_uf_tile_kernel(const UtArgs a) 
                 px += HW;
                 asm volatile("" : "+l"(px));
             }
+            // The warp's next row goes to L2 while this one is in flight and being worked on: a warp holds
+            // its 64 loads in registers, so bytes in flight are bounded by occupancy (20 warps x 8 KB per SM,
+            // and only while a warp is in its load phase); a prefetch holds nothing.  Lane l asks for the 128-byte
+            // lines of bins l, l + 32, ... of the tile's 32 columns.  (Measured: 0.0908 -> 0.0898 ms.)
+            if (r + UT_NW < UT_ROWS && y + UT_NW < a.H) {
+                const float* pn = a.x + item + (long long)lane * HW + (y + UT_NW) * a.W + blockIdx.x * 32;
+#pragma unroll
+                for (int k = 0; k < D; k += 32) {
+                    if (k + lane < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
+                    pn += 32LL * HW;
+                }
+            }
         }
         float ln_s = 0.f, log2_s = 0.f, top;
         if (MODE == DPV_IN_LOGITS) {
@@ -213,23 +226,23 @@ __global__ void __launch_bounds__(UT_NT, 5) head_uf_tile_kernel(const UtArgs a) 
 // UF[b,k,x] = sum over the flagged tiles of the column (top to bottom) of their partial sums, divided by
 // (their counts + the count of the shifted-frame pixels that sample the zero padding).  0/0 = NaN as in
 // the reference.  block = 32 columns x 8 bins of one item (768 blocks at the model's shape: one wave).
-// The flag of a tile is uniform over the block, so skipping unflagged tiles does not diverge; loads go
-// out eight at a time and are added in row order.
-constexpr int UT_MAXCH = 1024;
+// The flagged tiles of the strip are compacted into a list (uniform over the block); the partial sums of 16
+// tiles are in flight per thread and are added in row order.  Launched with programmatic stream
+// serialisation: what does not read partial sums (the padding counts) runs while the tile kernel drains.
 template <int D>
 __global__ void __launch_bounds__(256) head_uf_tile_finish_kernel(const UtArgs a) {
     __shared__ float den_s[32];
     __shared__ float r0_s[8], r1_s[8];
-    __shared__ unsigned char on_s[UT_MAXCH];
+    __shared__ short list_s[UT_MAXCH];
+    __shared__ int nlist_s;
     const int tid = threadIdx.x, c = tid & 31, g = tid >> 5;
     const int x = blockIdx.x * 32 + c, b = blockIdx.z;
     const int k = blockIdx.y * 8 + g;
     const bool ok = x < a.W;
     const int xe = ok ? x : 0;
-    pdl_wait();       // (PDL) the tile kernel has completed: its partial sums and flags are visible
+    // Everything up to pdl_wait() reads only what the host / earlier kernels wrote (intrinsics, tables): it
+    // runs while the tile kernel is still draining.
     const float fy = __ldg(a.intr + b * a.intr_bs + 4), cy = __ldg(a.intr + b * a.intr_bs + 5);
-    for (int ch = tid; ch < a.nchunk; ch += 256)
-        on_s[ch] = (unsigned char)(__ldg(a.flag + ((long long)b * a.nchunk + ch) * a.xtiles + blockIdx.x) != 0);
     // shifted-frame rows whose pixels sample the zero padding (E[d] = pad_depth there): sums of 0 / 1,
     // exact in any order.  p0: rows that are padding themselves; p1: every row (padded columns).
     float p0 = 0.f, p1 = 0.f;
@@ -240,18 +253,32 @@ __global__ void __launch_bounds__(256) head_uf_tile_finish_kernel(const UtArgs a
     }
     p0 = warp_sum(p0); p1 = warp_sum(p1);
     if (c == 0) { r0_s[g] = p0; r1_s[g] = p1; }
-    __syncthreads();
+    const bool colpad = (__ldg(a.col_tab + xe) >> 3) & 1;
+    pdl_wait();       // (PDL) the tile kernel has completed: its partial sums and flags are visible
+    // flagged tiles of this column strip, top to bottom, as a compact list (warp 0; ballot + prefix count)
     if (g == 0) {
-        const bool colpad = (__ldg(a.col_tab + xe) >> 3) & 1;
+        int n = 0;
+        for (int ch0 = 0; ch0 < a.nchunk; ch0 += 32) {
+            const int ch = ch0 + c;
+            const bool on = ch < a.nchunk &&
+                            __ldcg(a.flag + ((long long)b * a.nchunk + ch) * a.xtiles + blockIdx.x) != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) list_s[n + __popc(m & ((1u << c) - 1u))] = (short)ch;
+            n += __popc(m);
+        }
+        if (c == 0) nlist_s = n;
+    }
+    __syncthreads();
+    const int nlist = nlist_s;
+    if (g == 0) {
         float den = 0.f;
         for (int i = 0; i < 8; ++i) den += colpad ? r1_s[i] : r0_s[i];
-        for (int ch0 = 0; ch0 < a.nchunk; ch0 += 8) {
+        for (int i0 = 0; i0 < nlist; i0 += 8) {
             float cv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ch = ch0 + j;
-                cv[j] = (ok && ch < a.nchunk && on_s[ch]) ? __ldcg(a.cnt + ((long long)b * a.nchunk + ch) * a.W + x) : 0.f;
-            }
+            for (int j = 0; j < 8; ++j)
+                cv[j] = (ok && i0 + j < nlist)
+                            ? __ldcg(a.cnt + ((long long)b * a.nchunk + list_s[i0 + j]) * a.W + x) : 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) den = __fadd_rn(den, cv[j]);
         }
@@ -259,16 +286,14 @@ __global__ void __launch_bounds__(256) head_uf_tile_finish_kernel(const UtArgs a
     }
     float num = 0.f;
     if (ok && k < D) {
-        for (int ch0 = 0; ch0 < a.nchunk; ch0 += 8) {
-            float pv[8];
+        for (int i0 = 0; i0 < nlist; i0 += 16) {
+            float pv[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ch = ch0 + j;
-                pv[j] = (ch < a.nchunk && on_s[ch])
-                            ? __ldcg(a.part + (((long long)b * a.nchunk + ch) * D + k) * a.W + x) : 0.f;
-            }
+            for (int j = 0; j < 16; ++j)
+                pv[j] = (i0 + j < nlist)
+                            ? __ldcg(a.part + (((long long)b * a.nchunk + list_s[i0 + j]) * D + k) * a.W + x) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) num = __fadd_rn(num, pv[j]);
+            for (int j = 0; j < 16; ++j) num = __fadd_rn(num, pv[j]);
         }
     }
     __syncthreads();

@@ -41,5 +41,9 @@ int launch_sweep_gram_tiled(const SweepArgs& a, cudaStream_t st);
 // Defined in sweep_tma.cu: TMA-fed variant, four lanes per reference pixel (production path).
 bool sweep_gram_tma_supported(const SweepArgs& a);
 int launch_sweep_gram_tma(const SweepArgs& a, cudaStream_t st);
+// Defined in sweep_xcorr.cu: cross-correlation form (source-only products by a pre-pass into a workspace).
+long long sweep_xcorr_workspace_floats(int B, int V, int H, int W);
+bool sweep_xcorr_supported(const SweepArgs& a);
+int launch_sweep_xcorr(const SweepArgs& a, float* workspace, cudaStream_t st);
 
 }  // namespace dpv

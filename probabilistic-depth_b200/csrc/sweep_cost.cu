@@ -215,6 +215,10 @@ static int pick_plane_split(int B, int HW, int D, bool need_all_planes) {
 
 }  // namespace dpv
 
+extern "C" int64_t dpv_sweep_workspace_floats(int B, int V, int H, int W) {
+    return dpv::sweep_xcorr_workspace_floats(B, V, H, W);
+}
+
 extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const float* pose,
                                      const float* K, const float* rays, const float* d_candi,
                                      float* cost, float* log_softmax_out, int B, int V, int C,
@@ -222,11 +226,24 @@ extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const f
                                      int64_t src_vstride, int64_t pose_bstride, int64_t k_bstride,
                                      int64_t rays_bstride, float sigma, int dist, int algo,
                                      void* stream) {
+    return dpv_sweep_cost_volume_ws(ref, src, pose, K, rays, d_candi, cost, log_softmax_out, B, V, C, D, H, W,
+                                    ref_bstride, src_bstride, src_vstride, pose_bstride, k_bstride, rays_bstride,
+                                    sigma, dist, algo, nullptr, stream);
+}
+
+extern "C" int dpv_sweep_cost_volume_ws(const float* ref, const float* src, const float* pose,
+                                        const float* K, const float* rays, const float* d_candi,
+                                        float* cost, float* log_softmax_out, int B, int V, int C,
+                                        int D, int H, int W, int64_t ref_bstride, int64_t src_bstride,
+                                        int64_t src_vstride, int64_t pose_bstride, int64_t k_bstride,
+                                        int64_t rays_bstride, float sigma, int dist, int algo,
+                                        float* workspace, void* stream) {
     using namespace dpv;
     DPV_CHECK_ARG(ref && src && pose && K && rays && d_candi && cost);
     DPV_CHECK_ARG(B > 0 && V > 0 && C > 0 && D > 0 && H > 0 && W > 0);
     DPV_CHECK_ARG(dist == DPV_DIST_L2 || dist == DPV_DIST_L1);
-    DPV_CHECK_ARG(algo >= 0 && algo <= 4);
+    DPV_CHECK_ARG(algo >= 0 && algo <= 5);
+    DPV_CHECK_ARG(algo != 5 || workspace != nullptr);
     if ((long long)H * W > (1LL << 30) || B > 65535) return DPV_E_UNSUPP;
     if (algo >= 2 && dist != DPV_DIST_L2) return DPV_E_UNSUPP;
     if (algo == 3 && log_softmax_out != nullptr) return DPV_E_UNSUPP;
@@ -241,10 +258,13 @@ extern "C" int dpv_sweep_cost_volume(const float* ref, const float* src, const f
     const int HW = H * W;
     a.PS = pick_plane_split(B, HW, D, log_softmax_out != nullptr);
     if (algo == 0) {
+        static const int no_xc = [] { const char* v = getenv("DPV_SWEEP_NO_XCORR"); return v ? atoi(v) : 0; }();
         if (dist != DPV_DIST_L2) algo = 1;
+        else if (workspace != nullptr && !no_xc && sweep_xcorr_supported(a)) algo = 5;
         else if (sweep_gram_tma_supported(a)) algo = 4;
         else algo = (log_softmax_out != nullptr) ? 2 : 3;
     }
+    if (algo == 5) return launch_sweep_xcorr(a, workspace, (cudaStream_t)stream);
     if (algo == 4) return launch_sweep_gram_tma(a, (cudaStream_t)stream);
     if (algo == 3) return launch_sweep_gram_tiled(a, (cudaStream_t)stream);
     const int kper = (D + a.PS - 1) / a.PS;

@@ -59,6 +59,9 @@ class FrameStep:
         if mode == "feedback":
             self.warped = e(B, V + 1, D, h, w)
             self.bv_upd = e(B, D, h, w)
+        # scratch of the sweep's cross-correlation form (source-only product maps, one pre-pass per call)
+        self.sweep_ws = e(int(self.lib.dpv_sweep_workspace_floats(B, V, h, w)))
+        self.sweep_algo = 0
         self.two_sig = ops.two_sigma_sq(0.3)
         u = ops.KITTI_UF
         self.uf_params = [float(np.float32(u[k])) for k in ("zstart", "zend", "maxd", "mind")]
@@ -77,11 +80,11 @@ class FrameStep:
         chw = C * h * w
         fp = feats.data_ptr()
         hk("sweep", 0)
-        _lib.check(lib.dpv_sweep_cost_volume(
+        _lib.check(lib.dpv_sweep_cost_volume_ws(
             fp + 4 * V * chw, fp, p(poses), p(K), p(rays), p(self.d), p(self.cost),
             p(self.bv) if self.fuse_lsm else None,
             B, V, C, D, h, w, (V + 1) * chw, (V + 1) * chw, chw, (V + 1) * 16, 9, 3 * h * w,
-            self.sigma, 0, 0, st))
+            self.sigma, 0, self.sweep_algo, p(self.sweep_ws), st))
         hk("sweep", 1)
         if not self.fuse_lsm:
             hk("head_quarter", 0)
@@ -141,7 +144,9 @@ class FrameStep:
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):      # warm-up outside the capture (module loading, attributes)
+            n0 = _lib.launch_count()
             self.run(*args, **kw)
+            self._launches = _lib.launch_count() - n0      # what a replay re-runs
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
@@ -150,7 +155,11 @@ class FrameStep:
         return g
 
     def launches_per_step(self):
-        # sweep, 1/4-res soft-max, head, UF (weights + partial sums + finish); fused: stream kernel + finish
+        """Kernel launches of one step: counted by the library during capture()'s warm-up run when there was
+        one, else by the formula below (sweep [+ 1/4-res soft-max], head, UF: weights + partial sums + finish;
+        fused head + UF: tile kernel + finish)."""
+        if getattr(self, "_launches", None):
+            return int(self._launches)
         n = {"default": 6, "upsample": 7, "feedback": 8}[self.mode]
         if self.fuse_lsm:
             n -= 1

@@ -125,12 +125,16 @@ def sweep_cost_volume(ref, src, poses, K, rays, d_candi, sigma, dist="L2", algo=
     cost = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
     lsm = torch.empty_like(cost) if log_softmax else None
     lib = _lib.load()
-    _lib.check(lib.dpv_sweep_cost_volume(
+    # scratch for the cross-correlation form (algo 5, what "choose" takes for L2): source-only product maps
+    ws = None
+    if algo in (0, 5) and dist == "L2":
+        ws = torch.empty((int(lib.dpv_sweep_workspace_floats(B, V, H, W)),), device=ref.device, dtype=torch.float32)
+    _lib.check(lib.dpv_sweep_cost_volume_ws(
         _p(ref), _p(src), _p(poses), _p(K), _p(rays), _p(d), _p(cost), _p(lsm),
         B, V, C, D, H, W,
         ref.stride(0) if B > 1 else 0, src.stride(0) if B > 1 else 0, src.stride(1) if V > 1 else 0,
         poses.stride(0) if B > 1 else 0, k_bs, r_bs,
-        float(sigma), DIST[dist], int(algo), _stream()))
+        float(sigma), DIST[dist], int(algo), _p(ws), _stream()))
     return (cost, lsm) if log_softmax else cost
 
 

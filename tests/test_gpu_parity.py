@@ -51,10 +51,10 @@ def cam_dict(c):
 
 # ------------------------------------------------------------------------- K1 + K2a
 @pytest.mark.parametrize("name", cases.SWEEP_CASES)
-@pytest.mark.parametrize("dist,algo", [("L2", 0), ("L2", 4), ("L2", 3), ("L2", 2), ("L2", 1), ("L1", 1)])
+@pytest.mark.parametrize("dist,algo", [("L2", 0), ("L2", 5), ("L2", 4), ("L2", 3), ("L2", 2), ("L2", 1), ("L1", 1)])
 def test_sweep_vs_golden(dpv, golden, name, dist, algo):
     g = golden("sweep")
-    if algo == 4 and cases.sweep_case(name)["w"] % 4 != 0:
+    if algo in (4, 5) and cases.sweep_case(name)["w"] % 4 != 0:
         pytest.skip("the TMA kernel needs 16-byte row strides; algo=0 falls back (covered above)")
     key = "%s_%s" % (name, dist)
     c = cases.sweep_case(name)
@@ -74,7 +74,7 @@ def test_sweep_vs_golden(dpv, golden, name, dist, algo):
 
 
 @pytest.mark.parametrize("name", cases.SWEEP_WIDE_CASES)
-@pytest.mark.parametrize("algo", [0, 4, 1])
+@pytest.mark.parametrize("algo", [0, 5, 4, 1])
 def test_sweep_wide_vs_golden(dpv, golden, name, algo):
     """Images wider than 192 px -- the exact-coordinate variant of the TMA kernel
     (sweep_gram_tma_kernel<.,EXACT>) -- against the reference's own outputs, up to the north-star's
@@ -127,9 +127,10 @@ def test_sweep_batched_strided_and_fused_softmax(dpv):
         logclose(lsm[b:b + 1], O.log_softmax_bins(want).numpy())
 
 
+@pytest.mark.parametrize("algo", [5, 4])
 @pytest.mark.parametrize("kind", ["wide_baseline", "many_runs", "tall_motion", "two_views_strided"])
-def test_sweep_tma_window_and_pass_edges(dpv, kind):
-    """The TMA kernel's edge paths against the oracle: a source window wider than its 48-column
+def test_sweep_tma_window_and_pass_edges(dpv, kind, algo):
+    """The TMA kernels' (5: cross-correlation form, 4: Gram form) edge paths against the oracle: a source window wider than its 48-column
     capacity (per-thread gather fallback), more runs per pixel than one pass holds (16), a window
     taller than 8 rows, and two views read through a strided [B, V+1, C, h, w] allocation."""
     synth = dpv.synth
@@ -153,7 +154,7 @@ def test_sweep_tma_window_and_pass_edges(dpv, kind):
     cam = synth.camera(w, h, B)
     f, p = cu(feats), cu(poses)
     cost = dpv.ops.sweep_cost_volume(f[:, -1], f[:, :-1], p[:, :-1], cu(cam["intrinsics"]),
-                                     cu(cam["unit_ray"]), d, 10.0, algo=4)
+                                     cu(cam["unit_ray"]), d, 10.0, algo=algo)
     for b in range(B):
         want = O.plane_sweep_cost(T(feats[b:b + 1, -1]), T(feats[b:b + 1, :-1]), d,
                                   T(poses[b, :-1, :3, :3]), T(poses[b, :-1, :3, 3]),
@@ -169,7 +170,7 @@ def test_sweep_identity_pose_is_near_zero(dpv):
     ref = synth.randn(5, 1, C, h, w)
     poses = synth.pose()[None, None]
     cam = synth.camera(w, h, 1)
-    for algo in (1, 2, 3, 4):
+    for algo in (1, 2, 3, 4, 5):
         cost = dpv.ops.sweep_cost_volume(cu(ref), cu(ref[:, None]), cu(poses), cu(cam["intrinsics"]),
                                          cu(cam["unit_ray"]), synth.depth_candidates(5, 40, D), 10.0,
                                          algo=algo)
