@@ -281,7 +281,21 @@ int dpv_pipeline_run(dpv_pipeline* p, const float* feats, const float* poses, co
                      const int* col_fwd, const int* col_inv, float sigma,
                      float* bv, float* depth, float* variance, int64_t* argmax, float* uf,
                      float* depth_zero, float* quarter);
-/* Bytes copied host->device and device->host by the last run(). */
+/* The same call split in two, so that consecutive batches overlap: submit() enqueues the copies and the
+ * kernels of one batch and returns; wait() blocks until the OLDEST outstanding submission has its results in
+ * host memory.  The handle stages two batches on the device: batch n + 1 is copied in while batch n computes
+ * and batch n - 1 is read back; a third submit() first waits for the oldest.  The host buffers of a submission
+ * (inputs and outputs) must stay untouched until its wait() has returned; pinned memory makes the copies
+ * asynchronous.  run() = submit() + wait() for everything outstanding.  wait() with nothing outstanding
+ * returns DPV_E_BADARG. */
+int dpv_pipeline_submit(dpv_pipeline* p, const float* feats, const float* poses, const float* K,
+                        const float* rays, const float* d_candi, const float* logits_full,
+                        const float* intr_up, const int* row_fwd, const int* row_inv,
+                        const int* col_fwd, const int* col_inv, float sigma,
+                        float* bv, float* depth, float* variance, int64_t* argmax, float* uf,
+                        float* depth_zero, float* quarter);
+int dpv_pipeline_wait(dpv_pipeline* p);
+/* Bytes copied host->device and device->host by the last submission. */
 int dpv_pipeline_last_bytes(const dpv_pipeline* p, int64_t* h2d, int64_t* d2h);
 
 #ifdef __cplusplus

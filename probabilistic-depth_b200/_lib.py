@@ -47,6 +47,8 @@ PROTOTYPES = {
     "dpv_pipeline_create": (_c_i, [ctypes.POINTER(ctypes.c_void_p)] + [_c_i] * 9),
     "dpv_pipeline_destroy": (_c_i, [ctypes.c_void_p]),
     "dpv_pipeline_run": (_c_i, [ctypes.c_void_p] + [_c_fp] * 11 + [_c_f] + [_c_fp] * 7),
+    "dpv_pipeline_submit": (_c_i, [ctypes.c_void_p] + [_c_fp] * 11 + [_c_f] + [_c_fp] * 7),
+    "dpv_pipeline_wait": (_c_i, [ctypes.c_void_p]),
     "dpv_pipeline_last_bytes": (_c_i, [ctypes.c_void_p, ctypes.POINTER(_c_i64),
                                        ctypes.POINTER(_c_i64)]),
 }

@@ -50,6 +50,11 @@ constexpr int XC_MAXITEM = 128;                  // (row, dx-group, pixel-group)
 constexpr int XC_NMAP = 5;                       // source-only product maps per source image
 constexpr int XC_PRE_NT = 256, XC_PRE_SL = XC_PRE_NT / 32;   // pre-pass: 32 positions x 8 channel slices
 
+struct XcMaps {
+    CUtensorMap src[XC_WR];   // box {XC_WC cols, h rows, XC_CK channels} for h = 1 .. XC_WR: one copy per chunk
+    CUtensorMap ref;          // box {32 pixels, 1 row, XC_CK channels}
+};
+
 struct XcShared {
     int dx[2];         // min / max over the tile of (cell x0 - pixel x)
     int yy[2];         // min / max of cell y0
@@ -135,7 +140,7 @@ long long sweep_xcorr_workspace_floats(int B, int V, int H, int W) {
 template <bool EXACT, int MINB>
 __global__ void __launch_bounds__(XC_NT, MINB)
 sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
-                   const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_ref) {
+                   const __grid_constant__ XcMaps maps) {
     __shared__ __align__(128) float area[XC_AREA];                     // TMA stage ring, then P[row][dx][pixel]
     extern __shared__ __align__(16) float out_s[];                     // [kper][PX] result tile
     __shared__ float geo_s[20];          // K R (9), K t (3), cx, cy, 1/cx, 1/cy of the view; d range
@@ -235,7 +240,13 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
                 // an end point outside the image: clamp its cell to the image border cells -- every in-image
                 // cell of the segment still lies between the two clamped end cells
                 if (tap.x0 > -1000000) {
-                    const int ex = min(max(tap.x0, -1), a.W - 1), ey = min(max(tap.y0, -1), a.H - 1);
+                    // a position within the border slack below an integer counts for the upper cell (phase 3
+                    // puts every plane into a band cell it is within the slack of): a coordinate that is
+                    // constant along the ray up to rounding -- the row, in rectified stereo -- then costs one
+                    // cell row instead of two
+                    const int sx = tap.x0 + (tap.fx > 1.0f - kCellSlack ? 1 : 0);
+                    const int sy = tap.y0 + (tap.fy > 1.0f - kCellSlack ? 1 : 0);
+                    const int ex = min(max(sx, -1), a.W - 1), ey = min(max(sy, -1), a.H - 1);
                     cx0 = cx1 = ex - x; cy0 = cy1 = ey;
                     (void)inside;
                 } else {
@@ -290,7 +301,10 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
             const int ig = it & 7, rest = it >> 3;                        // rest = row * ng8 + dx group, < 16
             const int ir = ng8 == 1 ? rest : (ng8 == 2 ? rest >> 1 : (rest * 11) >> 5);
             const int im = rest - ir * ng8;
-            const int s_off = ir * XC_ROW + 4 * ig + 8 * im + cw * cpp * XC_WC;
+            // stage layout (the order a bulk tensor copy writes its box): [channel][row][col], then the
+            // reference pixels [channel][pixel]
+            const int chs = wh * XC_WC;                                   // channel stride of the window
+            const int s_off = cw * cpp * chs + ir * XC_WC + 4 * ig + 8 * im;
             const int r_off = wh * XC_ROW + 4 * ig + cw * cpp * TM_PX;
             float acc[4][8];
 #pragma unroll
@@ -298,22 +312,20 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
 #pragma unroll
                 for (int u = 0; u < 8; ++u) acc[j][u] = 0.f;
 
-            int s_issue = 0;
+            // chunk c is issued by lane 0 of warp c % 4 into stage c % ns
             auto issue = [&](int chunk) {
-                const int s = s_issue;
-                s_issue = (s_issue + 1 == ns) ? 0 : s_issue + 1;
+                const int s = chunk % ns;
                 float* st = area + s * stage_floats;
                 // the ring is also used through the generic proxy (the correlation tile, the soft-max partials):
                 // those accesses are ordered before this point by __syncthreads; this fence orders them before
                 // the async-proxy writes of the bulk copies
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tm_mbar_expect_tx(&full_bar[s], (unsigned)(stage_floats * sizeof(float)));
-                for (int r = 0; r < wh; ++r)
-                    tm_load_5d(st + r * XC_ROW, &map_src, wx0, wy0 + r, chunk * XC_CK, v, b, &full_bar[s]);
-                tm_load_4d(st + wh * XC_ROW, &map_ref, tx * TM_PX, y, chunk * XC_CK, b, &full_bar[s]);
+                tm_load_5d(st, &maps.src[wh - 1], wx0, wy0, chunk * XC_CK, v, b, &full_bar[s]);
+                tm_load_4d(st + wh * XC_ROW, &maps.ref, tx * TM_PX, y, chunk * XC_CK, b, &full_bar[s]);
             };
-            if (tid == 0) {
-                for (int c = 0; c < ns; ++c) issue(c);
+            if (lane == 0) {
+                for (int c = t; c < ns; c += XC_T) issue(c);
             }
             int s_use = 0;
             for (int chunk = 0; chunk < nchunk; ++chunk) {
@@ -327,9 +339,9 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
 #pragma unroll 2
                     for (int c = 0; c < cpp; ++c) {
                         const float4 r4 = *reinterpret_cast<const float4*>(rp + c * TM_PX);
-                        const float4 s0 = *reinterpret_cast<const float4*>(sp + c * XC_WC);
-                        const float4 s1 = *reinterpret_cast<const float4*>(sp + c * XC_WC + 4);
-                        const float4 s2 = *reinterpret_cast<const float4*>(sp + c * XC_WC + 8);
+                        const float4 s0 = *reinterpret_cast<const float4*>(sp + c * chs);
+                        const float4 s1 = *reinterpret_cast<const float4*>(sp + c * chs + 4);
+                        const float4 s2 = *reinterpret_cast<const float4*>(sp + c * chs + 8);
                         const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
                         const float sv[12] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
@@ -339,7 +351,7 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
                     }
                 }
                 __syncthreads();   // every warp is done with this stage
-                if (tid == 0 && chunk + ns < nchunk) issue(chunk + ns);
+                if (lane == 0 && chunk + ns < nchunk && ((chunk + ns) & (XC_T - 1)) == t) issue(chunk + ns);
             }
             // partial correlations -> shared memory, one copy per channel part: [cw][row][dx][pixel]
             const int psize = nitem * TM_PX;      // = wh * ndxp * 32
@@ -486,18 +498,20 @@ int launch_sweep_xcorr(const SweepArgs& a, float* workspace, cudaStream_t st) {
     tm_encode_fn enc = tm_encoder();
     const int kper = (a.D + a.PS - 1) / a.PS;
     const cuuint64_t chw = (cuuint64_t)a.C * a.H * a.W;
-    CUtensorMap msrc, mref;
+    XcMaps maps;
     {
         const cuuint64_t vs = a.V > 1 ? (cuuint64_t)a.src_vs : chw;
         const cuuint64_t bs = a.B > 1 ? (cuuint64_t)a.src_bs : vs * a.V;
         const cuuint64_t gdim[5] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.V, (cuuint64_t)a.B};
         const cuuint64_t gstr[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4, vs * 4, bs * 4};
-        const cuuint32_t box[5] = {XC_WC, 1, XC_CK, 1, 1};
         const cuuint32_t est[5] = {1, 1, 1, 1, 1};
-        if (enc(&msrc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(a.src), gdim, gstr, box, est,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return DPV_E_UNSUPP;
+        for (int hgt = 1; hgt <= XC_WR; ++hgt) {
+            const cuuint32_t box[5] = {XC_WC, (cuuint32_t)hgt, XC_CK, 1, 1};
+            if (enc(&maps.src[hgt - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(a.src), gdim, gstr, box, est,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return DPV_E_UNSUPP;
+        }
     }
     {
         const cuuint64_t bs = a.B > 1 ? (cuuint64_t)a.ref_bs : chw;
@@ -505,7 +519,7 @@ int launch_sweep_xcorr(const SweepArgs& a, float* workspace, cudaStream_t st) {
         const cuuint64_t gstr[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4, bs * 4};
         const cuuint32_t box[4] = {TM_PX, 1, XC_CK, 1};
         const cuuint32_t est[4] = {1, 1, 1, 1};
-        if (enc(&mref, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.ref), gdim, gstr, box, est,
+        if (enc(&maps.ref, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.ref), gdim, gstr, box, est,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return DPV_E_UNSUPP;
@@ -525,7 +539,7 @@ int launch_sweep_xcorr(const SweepArgs& a, float* workspace, cudaStream_t st) {
     // coordinates: reference operation order for wide images (see tm_coord), SFU form otherwise
     const bool exact = exact_env >= 0 ? (exact_env != 0) : (a.W > 192 || a.H > 192);
     cudaError_t e;
-    static const int minb = [] { const char* v = getenv("DPV_XC_MINB"); return v ? atoi(v) : 6; }();
+    static const int minb = [] { const char* v = getenv("DPV_XC_MINB"); return v ? atoi(v) : 5; }();
     // (PDL) the sweep kernel becomes resident behind the pre-pass and waits for it only where it first reads
     // the maps: the band and the correlation do not need them
 #define DPV_XC_GO(EX_, MB_)                                                                                      \
@@ -533,7 +547,7 @@ int launch_sweep_xcorr(const SweepArgs& a, float* workspace, cudaStream_t st) {
         e = cudaFuncSetAttribute(sweep_xcorr_kernel<EX_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return (int)e;                                                                     \
         e = dpv_launch_pdl(sweep_xcorr_kernel<EX_, MB_>, grid, block, smem, st, a, (const float*)smaps,          \
-                           (const float*)refn, msrc, mref);                                                      \
+                           (const float*)refn, maps);                                                      \
     } while (0)
     if (exact && minb == 5) DPV_XC_GO(true, 5);
     else if (exact) DPV_XC_GO(true, 6);

@@ -45,9 +45,22 @@ class FramePipeline:
                     quarter=mk((B, D, H // 4, W // 4)))
 
     def run(self, feats, poses, K, rays, d_candi, logits_full, intr_up, sigma, out):
+        """One batch, synchronously: returns when `out` holds the results (dpv_pipeline_run)."""
+        return self._call("dpv_pipeline_run", feats, poses, K, rays, d_candi, logits_full, intr_up, sigma, out)
+
+    def submit(self, feats, poses, K, rays, d_candi, logits_full, intr_up, sigma, out):
+        """Enqueue one batch and return (dpv_pipeline_submit).  Up to two batches are in flight: the next one is
+        copied in while this one computes.  Inputs and `out` must stay untouched until the matching wait()."""
+        return self._call("dpv_pipeline_submit", feats, poses, K, rays, d_candi, logits_full, intr_up, sigma, out)
+
+    def wait(self):
+        """Block until the oldest outstanding submission has its results in host memory."""
+        _lib.check(_lib.load().dpv_pipeline_wait(self._h))
+
+    def _call(self, entry, feats, poses, K, rays, d_candi, logits_full, intr_up, sigma, out):
         d32 = np.ascontiguousarray(np.asarray(d_candi, dtype=np.float32))
         rf, ri, cf, ci = self.luts
-        _lib.check(_lib.load().dpv_pipeline_run(
+        _lib.check(getattr(_lib.load(), entry)(
             self._h, _host_ptr(feats), _host_ptr(poses), _host_ptr(K), _host_ptr(rays),
             d32.ctypes.data, _host_ptr(logits_full), _host_ptr(intr_up),
             rf.ctypes.data, ri.ctypes.data, cf.ctypes.data, ci.ctypes.data, float(sigma),

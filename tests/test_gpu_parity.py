@@ -456,3 +456,36 @@ def test_host_pipeline_matches_ops(dpv):
     np.testing.assert_allclose(out["uf"].numpy(), uf.cpu().numpy(), rtol=1e-5, atol=1e-30, equal_nan=True)
     np.testing.assert_allclose(out["depth_zero"].numpy(), dz.cpu().numpy(), rtol=1e-5, atol=0)
     pipe.close()
+
+
+def test_host_pipeline_submit_wait_overlaps_batches_with_identical_results(dpv):
+    """dpv_pipeline_submit / dpv_pipeline_wait: four batches through the two staging slots, two in flight at a
+    time, each bit-identical to the same batch through the synchronous dpv_pipeline_run."""
+    B, V, C, D, h, w, H, W = 2, 1, 67, 64, 16, 24, 64, 96
+    synth = dpv.synth
+    d = synth.depth_candidates(5, 40, D)
+    cam = synth.camera(w, h, B)
+    from importlib import import_module
+    pl = import_module("probabilistic-depth_b200.pipeline")
+    pipe = pl.FramePipeline(B, V, C, D, h, w, H, W)
+    pin = lambda a: T(a).pin_memory()
+    const = [pin(synth.stereo_poses(B)), pin(cam["intrinsics"]), pin(cam["unit_ray"]), pin(cam["intrinsics_up"])]
+    batches = [(pin(synth.randn(300 + i, B, V + 1, C, h, w)),
+                pin(synth.ground_plane_logits(400 + i, B, H, W, d, cam["intrinsics_up"][0]))) for i in range(4)]
+    want = []
+    for f, lg in batches:
+        o = pipe.run(f, const[0], const[1], const[2], d, lg, const[3], 10.0, pipe.outputs())
+        want.append({k: v.clone() for k, v in o.items()})
+    with pytest.raises(dpv.DpvError):
+        pipe.wait()                                   # nothing outstanding
+    outs = [pipe.outputs() for _ in batches]
+    for i, (f, lg) in enumerate(batches):             # the third submit waits for the first internally
+        pipe.submit(f, const[0], const[1], const[2], d, lg, const[3], 10.0, outs[i])
+    pipe.wait()
+    pipe.wait()                                       # two were still outstanding
+    with pytest.raises(dpv.DpvError):
+        pipe.wait()
+    for o, wnt in zip(outs, want):
+        for k in wnt:
+            assert torch.equal(torch.nan_to_num(o[k].float(), nan=-7.0), torch.nan_to_num(wnt[k].float(), nan=-7.0)), k
+    pipe.close()

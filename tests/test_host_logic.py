@@ -151,6 +151,10 @@ def test_bench_reference_arm_prints_one_contract_line():
               "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference" = the imported, unmodified reference (here: /root/reference or baseline/_ref); "port" only where
+    # no reference tree exists
+    from oracle import reference_loader
+    assert d["cpu_baseline"]["kind"] == ("reference" if reference_loader.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]

@@ -1,34 +1,23 @@
 #!/bin/bash
-# One gpurun call: GPU parity tests, smoke, bench (both arms), per-kernel timings, ncu launch list
-# and one `--set full` capture of the dominant kernels.  Everything lands in gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh'
-set -u
-O=gpurun_out
-mkdir -p $O
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit,memory.total --format=csv > $O/gpu.csv 2>&1
-echo "== pytest -m gpu"
-timeout 900 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log
-tail -3 $O/pytest_gpu.log
-echo "== smoke"
-timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $O/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/smoke.log
-tail -2 $O/smoke.log
-echo "== bench"
-timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"
-timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"
-timeout 600 python bench.py --no-fuse-uf --no-cpu-baseline > $O/bench_n1_unfused.json 2> $O/bench_n1_unfused.err; echo "bench unfused rc=$?"
-cat $O/bench_n1.json $O/bench_n1_unfused.json $O/bench_ref.json
-echo "== per-kernel"
-timeout 600 python tools/bench_kernels.py > $O/kernels.log 2>&1; echo "kernels rc=$?"
-timeout 600 python tools/bench_kernels.py --graph > $O/kernels_graph.log 2>&1; echo "kernels graph rc=$?"
-grep -v '^{' $O/kernels_graph.log
-if [ "${SKIP_NCU:-0}" != "1" ]; then
-echo "== ncu launch list (same command as the bench, 2 steps)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/launches_bench.log 2>&1
-echo "launches rc=$?"
-echo "== ncu full"
-N=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'head_kernel|head_uf|sweep|ufield|uf_' \
-    -c 12 -f -o $O/prof_step python tools/run_once.py > $O/ncu_full.log 2>&1
-echo "ncu full rc=$?"
-fi
-ls -la $O
+# One GPU round (dev tool): full -m gpu suite, smoke, the contract bench and the other workloads.  Outputs -> gpurun_out/
+O=gpurun_out; mkdir -p $O
+nvidia-smi --query-gpu=index,name,clocks.max.sm,power.limit --format=csv > $O/gpu.csv
+python -m pytest tests -q -m gpu 2>&1 | tail -15 > $O/pytest_gpu.log; tail -4 $O/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
+python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; tail -3 $O/bench_n1.err
+python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"
+for w in feedback upsample stress large_d; do
+  python bench.py --workload $w --steps 50 > $O/bench_$w.json 2> $O/bench_$w.err; echo "$w rc=$?"; tail -2 $O/bench_$w.err
+done
+python - <<'PY'
+import json
+for n in ("n1", "feedback", "upsample", "stress", "large_d"):
+    try:
+        d = json.loads(open("gpurun_out/bench_%s.json" % n).read())
+        print(n, "value %.0f  ms %.4f  roofline %.3f  frame_hbm %.3f  survey_hbm %.3f  e2e %.0f (%.2f of ceiling)  incumbent %s  cpu %s" % (
+            d["value"], d["ms_per_step"], d["roofline"]["frac"], d["config"]["frame_hbm_frac"], d["config"]["survey_hbm_frac"],
+            d["e2e"]["value"], d["e2e"]["frac_of_ceiling"], d.get("incumbent", {}).get("value"), d.get("cpu_baseline", {}).get("value")))
+        print("   kernels", {k: round(v["ms"], 4) for k, v in d["kernels"].items()})
+    except Exception as e:
+        print(n, "failed", e)
+PY
