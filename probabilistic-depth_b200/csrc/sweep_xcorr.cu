@@ -42,6 +42,7 @@ namespace dpv {
 
 constexpr int XC_T = 4, XC_NT = TM_PX * XC_T;
 constexpr int XC_WC = 56, XC_WR = 6;             // source window capacity (cols, rows)
+constexpr int XC_WCW = 96, XC_WRW = 3;           // wide window for few rows: 32 pixels + up to 64 column offsets
 constexpr int XC_CK = 8;                         // channels per chunk
 constexpr int XC_ROW = XC_CK * XC_WC;            // floats of one window row of a chunk
 constexpr int XC_AREA = 2 * (XC_WR * XC_ROW + XC_CK * TM_PX);   // stage ring / correlation tile (floats)
@@ -52,6 +53,8 @@ constexpr int XC_PRE_NT = 256, XC_PRE_SL = XC_PRE_NT / 32;   // pre-pass: 32 pos
 
 struct XcMaps {
     CUtensorMap src[XC_WR];   // box {XC_WC cols, h rows, XC_CK channels} for h = 1 .. XC_WR: one copy per chunk
+    CUtensorMap wide[XC_WRW]; // box {XC_WCW cols, h rows, XC_CK channels} for h = 1 .. XC_WRW (large images:
+                              // a long, flat disparity range, e.g. rectified stereo at full resolution)
     CUtensorMap ref;          // box {32 pixels, 1 row, XC_CK channels}
 };
 
@@ -166,22 +169,12 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
         for (int s = 0; s < XC_MAXSTAGE; ++s) tm_mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (t == 1) {    // smallest and largest plane depth of this block (the planes need not be sorted)
-        float lo = INFINITY, hi = -INFINITY;
-        for (int k = lane; k < nk; k += 32) {
-            const float dk = __ldg(a.d + k0 + k);
-            lo = fminf(lo, dk); hi = fmaxf(hi, dk);
-        }
-        lo = -warp_max(-lo); hi = warp_max(hi);
-        if (lane == 0) { geo_s[16] = lo; geo_s[17] = hi; geo_s[18] = __frcp_rn(a.sigma); }
-    }
+    if (tid == 64) geo_s[18] = __frcp_rn(a.sigma);
 
     const float* rays = a.rays + (long long)b * a.rays_bs;
     const float rx = __ldg(rays + p), ry = __ldg(rays + HW + p), rz = __ldg(rays + 2 * HW + p);
     const float* ref = a.ref + (long long)b * a.ref_bs;
     const int nchunk = (a.C + XC_CK - 1) / XC_CK;
-    const int kpt = (nk + XC_T - 1) >> 2;
-    const int wa = min(nk, t * kpt), wb = min(nk, wa + kpt);   // planes of this thread
     const int Wp = a.W + 2, MP = (a.H + 2) * Wp;
     unsigned stage_phase = 0;          // bit s: parity the next wait on stage s expects
     float rr = 0.f;                    // <r, r> of this pixel (read after the pre-pass has completed)
@@ -199,11 +192,7 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
             geo_s[tid] = c;
             geo_s[tid + 2] = __frcp_rn(c);
         }
-        if (tid == 32) {
-            ts.dx[0] = 1 << 30; ts.dx[1] = -(1 << 30); ts.yy[0] = 1 << 30; ts.yy[1] = -(1 << 30);
-            ts.wide = 0;
-        }
-        __syncthreads();   // geo_s, d_s, barrier init, ts; previous view done with area
+        __syncthreads();   // geo_s, d_s, barrier init; previous view done with area
         // (the per-pixel term and the view constants are rebuilt from shared memory where they are used, so that
         // they do not occupy registers across the correlation loop)
         auto load_geom = [&](PixelTerm& pt, TmGeom& g) {
@@ -215,6 +204,22 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
             g.half_w = (float)a.W * 0.5f; g.half_h = (float)a.H * 0.5f;
         };
 
+        // The planes are taken in blocks [cur, cur + len): a block is shrunk (halved) until its band fits the
+        // shared-memory window -- at the model's 64 x 96 the first block is all D planes; on a 256 x 384 or
+        // 384 x 1280 image the disparity range of all planes (40+ columns) does not fit and the near planes
+        // go in blocks of 4-8, the far ones in blocks of 16-32.  After a block that fitted, the next one is
+        // tried at twice its length.
+        int cur = 0, len = nk;
+        while (cur < nk) {
+        len = min(len, nk - cur);
+        if (tid == 32) {
+            ts.dx[0] = 1 << 30; ts.dx[1] = -(1 << 30); ts.yy[0] = 1 << 30; ts.yy[1] = -(1 << 30);
+            ts.wide = 0;
+        }
+        __syncthreads();   // ts; the previous block is done with the correlation tile in `area`
+        const int kpt = (len + XC_T - 1) >> 2;
+        const int wa = min(cur + len, cur + t * kpt), wb = min(cur + len, wa + kpt);   // planes of this thread
+
         // ---------------- 1. the band of the tile --------------------------------------------------
         // Along a ray the source coordinate is a linear-fractional function of the depth, hence monotone
         // between the smallest and the largest plane depth as long as the projective denominator keeps its
@@ -225,13 +230,20 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
         if (t < 2) {
             int cx0 = 1 << 30, cx1 = -(1 << 30), cy0 = 1 << 30, cy1 = -(1 << 30);
             bool wide = false;
+            // smallest and largest plane depth of the block (the planes need not be sorted)
+            float dmin = INFINITY, dmax = -INFINITY;
+            for (int k = cur + lane; k < cur + len; k += 32) {
+                const float dk = d_s[k];
+                dmin = fminf(dmin, dk); dmax = fmaxf(dmax, dk);
+            }
+            dmin = -warp_max(-dmin); dmax = warp_max(dmax);
             if (active) {
                 PixelTerm pt;
                 TmGeom g;
                 load_geom(pt, g);
-                const float dk = geo_s[16 + t];
+                const float dk = t == 0 ? dmin : dmax;
                 const float den = fmaf(pt.z, dk, g.t1z);
-                const float den_o = fmaf(pt.z, geo_s[17 - t], g.t1z);
+                const float den_o = fmaf(pt.z, t == 0 ? dmax : dmin, g.t1z);
                 wide = !(den > 1e-6f && den_o > 1e-6f);
                 float ix, iy;
                 tm_coord<EXACT>(g, pt, dk, ix, iy);
@@ -272,24 +284,37 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
         const int wh = any_cell ? ts.yy[1] + 2 - wy0 : 0;                   // taps reach y0 + 1
         const int nitem = wh * ng8 * 8;
         const int ndxp = 8 * ng8;
-        const bool fits = (ng8 <= (XC_WC - TM_PX) / 8) && (wh <= XC_WR) && (nitem <= XC_MAXITEM) && !ts.wide;
-        __syncthreads();   // ts is re-initialised at the top of the next view
+        // window width: 56 columns (up to 6 rows), or 96 columns when the band is long and flat (up to 3 rows)
+        const bool use_wide = (ng8 > (XC_WC - TM_PX) / 8) && (wh <= XC_WRW);
+        const int wc = use_wide ? XC_WCW : XC_WC;
+        const bool fits = (ng8 * 8 + TM_PX <= wc) && (wh <= XC_WR) && (nitem <= XC_MAXITEM) && !ts.wide;
+        const bool pole = ts.wide != 0;
+        __syncthreads();   // ts is re-initialised at the top of the next block
 
-        if (!fits) {
+        if (!fits) {       // (uniform across the CTA)
+            if (!pole && len > 1) {
+                len = (len + 1) >> 1;      // same start, half the planes
+                continue;
+            }
+            // a single plane whose band does not fit, or a pole of the projection inside the block: gather
             if (active && wa < wb) {
                 PixelTerm pt;
                 TmGeom g;
                 load_geom(pt, g);
                 tm_gather_planes<EXACT>(a.C, a.H, a.W, src, ref + p, g, pt, d_s, wa, wb, geo_s[18], out_s + px, v == 0);
             }
-            continue;   // next view (uniform across the CTA)
+            cur += len;
+            len = 2 * len;
+            continue;
         }
 
         // ---------------- 2. banded correlation of the tile ---------------------------------------
         if (nitem > 0) {
-            const int stage_floats = wh * XC_ROW + XC_CK * TM_PX;
-            // stages that fit the ring: XC_AREA / stage_floats for wh = 1..6
-            const int ns = min(wh == 1 ? 8 : wh == 2 ? 5 : wh == 3 ? 3 : 2, nchunk);
+            const int win_floats = wh * XC_CK * wc;
+            const int stage_floats = win_floats + XC_CK * TM_PX;
+            // stages that fit the ring: XC_AREA / stage_floats for wh = 1..6 (56 columns), 1..3 (96 columns)
+            const int ns = min(use_wide ? (wh == 1 ? 5 : wh == 2 ? 3 : 2) : (wh == 1 ? 8 : wh == 2 ? 5 : wh == 3 ? 3 : 2),
+                               nchunk);
             const int wx0 = tx * TM_PX + dlo;
             // warps split the items and, when there are few, the channels of a chunk
             const int iw_n = nitem <= 32 ? 1 : (nitem <= 64 ? 2 : 4);   // warps side by side on items
@@ -299,13 +324,13 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
             const bool has_item = item < nitem;
             const int it = has_item ? item : 0;
             const int ig = it & 7, rest = it >> 3;                        // rest = row * ng8 + dx group, < 16
-            const int ir = ng8 == 1 ? rest : (ng8 == 2 ? rest >> 1 : (rest * 11) >> 5);
+            const int ir = ng8 == 1 ? rest : (ng8 == 2 ? rest >> 1 : (ng8 == 3 ? (rest * 11) >> 5 : rest / ng8));
             const int im = rest - ir * ng8;
             // stage layout (the order a bulk tensor copy writes its box): [channel][row][col], then the
             // reference pixels [channel][pixel]
-            const int chs = wh * XC_WC;                                   // channel stride of the window
-            const int s_off = cw * cpp * chs + ir * XC_WC + 4 * ig + 8 * im;
-            const int r_off = wh * XC_ROW + 4 * ig + cw * cpp * TM_PX;
+            const int chs = wh * wc;                                      // channel stride of the window
+            const int s_off = cw * cpp * chs + ir * wc + 4 * ig + 8 * im;
+            const int r_off = win_floats + 4 * ig + cw * cpp * TM_PX;
             float acc[4][8];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -321,8 +346,9 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
                 // the async-proxy writes of the bulk copies
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tm_mbar_expect_tx(&full_bar[s], (unsigned)(stage_floats * sizeof(float)));
-                tm_load_5d(st, &maps.src[wh - 1], wx0, wy0, chunk * XC_CK, v, b, &full_bar[s]);
-                tm_load_4d(st + wh * XC_ROW, &maps.ref, tx * TM_PX, y, chunk * XC_CK, b, &full_bar[s]);
+                tm_load_5d(st, use_wide ? &maps.wide[wh - 1] : &maps.src[wh - 1], wx0, wy0, chunk * XC_CK, v, b,
+                           &full_bar[s]);
+                tm_load_4d(st + win_floats, &maps.ref, tx * TM_PX, y, chunk * XC_CK, b, &full_bar[s]);
             };
             if (lane == 0) {
                 for (int c = t; c < ns; c += XC_T) issue(c);
@@ -437,7 +463,9 @@ sweep_xcorr_kernel(const SweepArgs a, const float* smaps, const float* refn,
                 *o = (v == 0) ? val : (*o + val);
             }
         }
-        // (the next view's first __syncthreads orders these reads of `area` before its writes)
+        cur += len;
+        len = 2 * len;
+        }   // plane blocks (the next block's / view's first __syncthreads orders these reads of `area`)
     }
     // ---------------- 4. result tile -> global memory, one 128-byte row per warp-instruction ----
     if (!have_rr) pdl_wait();   // (tiles that only gathered) never complete ahead of the pre-pass
@@ -505,9 +533,11 @@ int launch_sweep_xcorr(const SweepArgs& a, float* workspace, cudaStream_t st) {
         const cuuint64_t gdim[5] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.V, (cuuint64_t)a.B};
         const cuuint64_t gstr[4] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4, vs * 4, bs * 4};
         const cuuint32_t est[5] = {1, 1, 1, 1, 1};
-        for (int hgt = 1; hgt <= XC_WR; ++hgt) {
-            const cuuint32_t box[5] = {XC_WC, (cuuint32_t)hgt, XC_CK, 1, 1};
-            if (enc(&maps.src[hgt - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(a.src), gdim, gstr, box, est,
+        for (int hgt = 1; hgt <= XC_WR + XC_WRW; ++hgt) {
+            const bool wide = hgt > XC_WR;
+            const cuuint32_t box[5] = {(cuuint32_t)(wide ? XC_WCW : XC_WC), (cuuint32_t)(wide ? hgt - XC_WR : hgt), XC_CK, 1, 1};
+            if (enc(wide ? &maps.wide[hgt - XC_WR - 1] : &maps.src[hgt - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                    const_cast<float*>(a.src), gdim, gstr, box, est,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return DPV_E_UNSUPP;

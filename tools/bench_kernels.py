@@ -153,6 +153,11 @@ def main():
         med, best = timeit(f, nrot)
         byt = B * (12 * h * w * D + 8 * h * w)
         res["bayes_fuse"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+        ad = [0.5 * torch.randn((B, D, h, w), device="cuda") for _ in range(nrot)]
+        f = lambda i: ops.head(bv[i], d, addend=ad[i], logp=True)
+        med, best = timeit(f, nrot)
+        byt = B * (12 * h * w * D)
+        res["feedback_fuse"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
         fr = [torch.randn((B, 2, D, h, w), device="cuda") for _ in range(nrot)]
         f = lambda i: ops.warp_feature(fr[i], poses, K, rays, d)
         med, best = timeit(f, nrot)
