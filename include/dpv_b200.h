@@ -199,25 +199,20 @@ int dpv_correlation(const float* x1, const float* x2, float* out, int B, int C, 
 
 /* ---- depth-plane sharding (large D) -----------------------------------------------------
  * Soft-max over planes that live on several GPUs (not in the reference).  Rank g
- * owns planes [plane_offset, plane_offset + D) of x [B, D, HW].  Sequence per rank, with the
- * host issuing the collectives (NCCL over NVLink) on the same stream between the calls:
- *   dpv_shard_max      -> all-reduce MAX of local_max [B*HW]        (local_argmax: all-gather)
- *   dpv_shard_sums     -> all-reduce SUM of sums [2, B*HW]  (sum exp(x-M), sum d exp(x-M))
- *   dpv_shard_central  -> all-reduce SUM of central [B*HW]  (sum (d-E)^2 exp(x-M)), optional
- *   dpv_shard_finish   -> logp = x - M - log S for the local planes; depth, variance replicated
- *   dpv_shard_argmax_merge: first-max-wins merge of the gathered (value, index) candidates.
+ * owns planes [plane_offset, plane_offset + D) of x [B, D, HW].  Sequence per rank, with the host issuing
+ * ONE collective (NCCL all-gather over NVLink) on the same stream between the two calls:
+ *   dpv_shard_stats        -> stats [5][B*HW]: local max m, S0 = sum exp(x - m), local mean mu = sum d exp / S0,
+ *                             local central moment M2 = sum (d - mu)^2 exp(x - m), index of the first local max
+ *   all-gather             -> gathered [G][5][B*HW], ranks in plane order
+ *   dpv_shard_merge_finish -> merges the G records per pixel (online-soft-max weights, pairwise variance rule,
+ *                             first-maximum-wins arg-max) and writes logp = x - M - log S for the local planes;
+ *                             depth / variance / argmax [B*HW] come out replicated on every rank.  Any of
+ *                             logp / depth / variance / argmax may be null.
  */
-int dpv_shard_max(const float* x, float* local_max, float* local_argmax, int B, int D, int HW,
-                  int plane_offset, void* stream);
-int dpv_shard_sums(const float* x, const float* d_local, const float* global_max, float* sums,
-                   int B, int D, int HW, void* stream);
-int dpv_shard_central(const float* x, const float* d_local, const float* global_max,
-                      const float* global_sums, float* central, int B, int D, int HW, void* stream);
-int dpv_shard_finish(const float* x, const float* global_max, const float* global_sums,
-                     const float* global_central, float* logp, float* depth, float* variance,
-                     int B, int D, int HW, void* stream);
-int dpv_shard_argmax_merge(const float* vals, const float* idx, int64_t* out, int G, int64_t n,
-                           void* stream);
+int dpv_shard_stats(const float* x, const float* d_local, float* stats, int B, int D, int HW,
+                    int plane_offset, void* stream);
+int dpv_shard_merge_finish(const float* x, const float* gathered, float* logp, float* depth,
+                           float* variance, int64_t* argmax, int G, int B, int D, int HW, void* stream);
 
 /* ---- eval metrics on the device ------------------------------------
  * dpv_depth_errors replaces img_utils.depth_error (utils/img_utils.py:17-22) around depthError

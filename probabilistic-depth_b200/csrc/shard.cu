@@ -2,176 +2,226 @@
 //
 // Not in the reference: it only ever soft-maxes D=64 planes on one device
 // (models/models.py:351,560; models/packnet.py:394).  When the D planes of a cost volume are
-// split over G GPUs, log_softmax over D needs one exchange: the per-pixel maximum (NCCL MAX),
-// then the per-pixel sums (NCCL SUM).  Each rank runs
-//     shard_max  -> all-reduce(max) -> shard_sums -> all-reduce(sum) -> shard_finish
-// and, when the variance is wanted, shard_central -> all-reduce(sum) before finish; the
-// collectives are issued by the host wrapper (torch.distributed / NCCL over NVLink) on the
-// same stream.  Payload per collective: 4 (or 8) bytes per pixel.  The kernels are streaming
-// passes over the local [B, D_local, HW] slice; HBM-bound (the re-reads hit L2 when the slice fits).
+// split over G GPUs, log_softmax over D (and E[d], Var, arg-max) needs ONE exchange.  Each rank runs
+//     shard_stats  ->  all-gather of the per-pixel statistics  ->  shard_merge_finish
+// * shard_stats: one pass over the local [B, D_local, HW] slice with the planes in registers (T adjacent
+//   lanes share a pixel): local maximum m, S0 = sum exp(x - m), the local mean mu = sum d exp / S0, the
+//   local central second moment M2 = sum (d - mu)^2 exp(x - m) and the index of the first local maximum --
+//   five floats per pixel, written as five planes [5][B*HW].
+// * the host all-gathers those 20 bytes per pixel (one NCCL collective over NVLink on the same stream).
+// * shard_merge_finish: per pixel the statistics of the G ranks are merged with the online-soft-max rule
+//   (w_g = S0_g exp(m_g - M)) and the pairwise-variance rule (M2 = sum [M2_g e^(m_g - M) + w_g (mu_g - mu)^2],
+//   no cancellation), the arg-max is the first rank attaining M, and the local planes of the log-softmax are
+//   written: logp = x - M - log S.
+// Two reads and one write of the local slice (the first version read it four times and used three
+// collectives: 3 ms per call at world 2; profiles/r01f_nccl_plane_shard.txt).  HBM-bound.
 #include "dpv_common.cuh"
 
 namespace dpv {
 
-constexpr int SH_NT = 256;
+constexpr int SH_NT = 128;
+constexpr int SH_NSTAT = 5;     // m, S0, mu, M2, arg-max (as float: exact below 2^24 planes)
 
-__global__ void __launch_bounds__(SH_NT) shard_max_kernel(const float* __restrict__ x,
-                                                          float* __restrict__ m, float* __restrict__ am,
-                                                          int D, int HW, int k_offset) {
+template <int T>
+__device__ __forceinline__ float sh_group_max(float v) {
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int T>
+__device__ __forceinline__ float sh_group_sum(float v) {
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int T>
+__device__ __forceinline__ int sh_group_min(int v) {
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// DL local planes, T lanes per pixel, DL / T planes per lane in registers: the slice is read once.
+template <int DL, int T>
+__global__ void __launch_bounds__(SH_NT) shard_stats_kernel(const float* __restrict__ x,
+                                                            const float* __restrict__ d,
+                                                            float* __restrict__ stats, int B, int HW,
+                                                            int k_offset) {
+    constexpr int DT = DL / T, PIX = SH_NT / T;
+    __shared__ float d_s[DL];
+    for (int k = threadIdx.x; k < DL; k += SH_NT) d_s[k] = __ldg(d + k);
+    __syncthreads();
+    const int b = blockIdx.y, r = threadIdx.x % T;
+    int q = blockIdx.x * PIX + threadIdx.x / T;
+    const bool live = q < HW;
+    q = live ? q : HW - 1;
+    const int kb = r * DT;
+    const float* px = x + ((long long)b * DL + kb) * HW + q;
+    float v[DT];
+#pragma unroll
+    for (int k = 0; k < DT; ++k) {
+        v[k] = ld_stream(px);
+        px += HW;
+        asm volatile("" : "+l"(px));
+    }
+    float m = v[0];
+#pragma unroll
+    for (int k = 1; k < DT; ++k) m = fmaxf(m, v[k]);
+    m = sh_group_max<T>(m);
+    int first = 1 << 30;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < DT; ++kk) {
+        const int k = DT - 1 - kk;                 // last first: the smallest index among equal maxima remains
+        first = (v[k] == m) ? kb + k : first;
+        v[k] = __expf(v[k] - m);
+        s0 += v[k];
+        s1 = fmaf(d_s[kb + k], v[k], s1);
+    }
+    s0 = sh_group_sum<T>(s0); s1 = sh_group_sum<T>(s1);
+    first = sh_group_min<T>(first);
+    const float mu = __fdiv_rn(s1, s0);
+    float m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < DT; ++k) {
+        const float c = d_s[kb + k] - mu;
+        m2 = fmaf(c * c, v[k], m2);
+    }
+    m2 = sh_group_sum<T>(m2);
+    if (live && r == 0) {
+        const long long n = (long long)B * HW, pix = (long long)b * HW + q;
+        stats[pix] = m; stats[n + pix] = s0; stats[2 * n + pix] = mu; stats[3 * n + pix] = m2;
+        stats[4 * n + pix] = (float)(first + k_offset);
+    }
+}
+
+// Any D_local: one thread per pixel, three passes over the pixel's planes (the later ones hit L2).
+__global__ void __launch_bounds__(SH_NT) shard_stats_generic_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ d,
+                                                                    float* __restrict__ stats, int B, int D,
+                                                                    int HW, int k_offset) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * SH_NT + threadIdx.x;
     if (q >= HW) return;
     const float* p = x + (long long)b * D * HW + q;
-    float best = -INFINITY;
-    int bk = 0;
+    float m = -INFINITY;
+    int first = 0;
     for (int k = 0; k < D; ++k) {
         const float v = __ldg(p + (long long)k * HW);
-        const bool take = (v > best) || (k == 0);
-        bk = take ? k : bk;
-        best = take ? v : best;
+        const bool take = (v > m) || (k == 0);
+        first = take ? k : first;
+        m = take ? v : m;
     }
-    m[(long long)b * HW + q] = best;
-    if (am != nullptr) am[(long long)b * HW + q] = (float)(bk + k_offset);
-}
-
-// sums[0] = sum exp(x - M), sums[1] = sum d exp(x - M), M the global per-pixel maximum.
-__global__ void __launch_bounds__(SH_NT) shard_sums_kernel(const float* __restrict__ x,
-                                                           const float* __restrict__ d,
-                                                           const float* __restrict__ gmax,
-                                                           float* __restrict__ sums, int B, int D,
-                                                           int HW) {
-    const int b = blockIdx.y;
-    const int q = blockIdx.x * SH_NT + threadIdx.x;
-    if (q >= HW) return;
-    const long long pix = (long long)b * HW + q;
-    const float* p = x + (long long)b * D * HW + q;
-    const float M = gmax[pix];
-    float s = 0.f, t = 0.f;
+    float s0 = 0.f, s1 = 0.f;
     for (int k = 0; k < D; ++k) {
-        const float e = expf(__ldg(p + (long long)k * HW) - M);
-        s += e;
-        t = fmaf(__ldg(d + k), e, t);
+        const float e = __expf(__ldg(p + (long long)k * HW) - m);
+        s0 += e;
+        s1 = fmaf(__ldg(d + k), e, s1);
     }
-    sums[pix] = s;
-    sums[(long long)B * HW + pix] = t;
-}
-
-// central[pix] = sum (d - E)^2 exp(x - M) with E = sums[1]/sums[0] (global sums).
-__global__ void __launch_bounds__(SH_NT) shard_central_kernel(const float* __restrict__ x,
-                                                              const float* __restrict__ d,
-                                                              const float* __restrict__ gmax,
-                                                              const float* __restrict__ sums,
-                                                              float* __restrict__ central, int B,
-                                                              int D, int HW) {
-    const int b = blockIdx.y;
-    const int q = blockIdx.x * SH_NT + threadIdx.x;
-    if (q >= HW) return;
-    const long long pix = (long long)b * HW + q;
-    const float* p = x + (long long)b * D * HW + q;
-    const float M = gmax[pix];
-    const float E = __fdiv_rn(sums[(long long)B * HW + pix], sums[pix]);
-    float c = 0.f;
+    const float mu = __fdiv_rn(s1, s0);
+    float m2 = 0.f;
     for (int k = 0; k < D; ++k) {
-        const float e = expf(__ldg(p + (long long)k * HW) - M);
-        const float dd = __ldg(d + k) - E;
-        c = fmaf(dd * dd, e, c);
+        const float e = __expf(__ldg(p + (long long)k * HW) - m);
+        const float c = __ldg(d + k) - mu;
+        m2 = fmaf(c * c, e, m2);
     }
-    central[pix] = c;
+    const long long n = (long long)B * HW, pix = (long long)b * HW + q;
+    stats[pix] = m; stats[n + pix] = s0; stats[2 * n + pix] = mu; stats[3 * n + pix] = m2;
+    stats[4 * n + pix] = (float)(first + k_offset);
 }
 
-__global__ void __launch_bounds__(SH_NT) shard_finish_kernel(const float* __restrict__ x,
-                                                             const float* __restrict__ gmax,
-                                                             const float* __restrict__ sums,
-                                                             const float* __restrict__ central,
-                                                             float* __restrict__ logp,
-                                                             float* __restrict__ depth,
-                                                             float* __restrict__ var, int B, int D,
-                                                             int HW) {
+// gathered [G][5][B*HW] (rank order = plane order).  One thread per pixel merges the G records, writes the
+// replicated per-pixel products and streams the local planes of the log-softmax.
+__global__ void __launch_bounds__(SH_NT) shard_merge_finish_kernel(const float* __restrict__ x,
+                                                                   const float* __restrict__ gathered,
+                                                                   float* __restrict__ logp,
+                                                                   float* __restrict__ depth,
+                                                                   float* __restrict__ var,
+                                                                   long long* __restrict__ argmax, int G, int B,
+                                                                   int D, int HW) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * SH_NT + threadIdx.x;
     if (q >= HW) return;
-    const long long pix = (long long)b * HW + q;
-    const float M = gmax[pix], S = sums[pix];
-    const float ls = logf(S);
+    const long long n = (long long)B * HW, pix = (long long)b * HW + q;
+    const long long gs = (long long)SH_NSTAT * n;
+    float M = -INFINITY, am = 0.f;
+    for (int g = 0; g < G; ++g) {
+        const float mg = gathered[g * gs + pix];
+        if (mg > M) { M = mg; am = gathered[g * gs + 4 * n + pix]; }    // strict: the first rank attaining M wins
+    }
+    float S = 0.f, s1 = 0.f;
+    for (int g = 0; g < G; ++g) {
+        const float w = gathered[g * gs + n + pix] * __expf(gathered[g * gs + pix] - M);
+        S += w;
+        s1 = fmaf(w, gathered[g * gs + 2 * n + pix], s1);
+    }
+    const float mean = __fdiv_rn(s1, S);
+    if (var != nullptr) {
+        float m2 = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const float sc = __expf(gathered[g * gs + pix] - M);
+            const float c = gathered[g * gs + 2 * n + pix] - mean;
+            m2 += gathered[g * gs + 3 * n + pix] * sc + gathered[g * gs + n + pix] * sc * c * c;
+        }
+        var[pix] = __fdiv_rn(m2, S);
+    }
+    if (depth != nullptr) depth[pix] = mean;
+    if (argmax != nullptr) argmax[pix] = (long long)am;
     if (logp != nullptr) {
+        const float ls = logf(S);
         const float* p = x + (long long)b * D * HW + q;
         float* o = logp + (long long)b * D * HW + q;
-        for (int k = 0; k < D; ++k)
-            st_stream(o + (long long)k * HW, (__ldg(p + (long long)k * HW) - M) - ls);
+        int k = 0;
+        for (; k + 8 <= D; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = ld_stream(p + (long long)(k + j) * HW);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_stream(o + (long long)(k + j) * HW, (v[j] - M) - ls);
+        }
+        for (; k < D; ++k) st_stream(o + (long long)k * HW, (ld_stream(p + (long long)k * HW) - M) - ls);
     }
-    if (depth != nullptr) depth[pix] = __fdiv_rn(sums[(long long)B * HW + pix], S);
-    if (var != nullptr && central != nullptr) var[pix] = __fdiv_rn(central[pix], S);
 }
 
-// First-maximum-wins merge of per-rank (value, index) candidates, ranks in plane order.
-__global__ void __launch_bounds__(SH_NT) shard_argmax_merge_kernel(const float* __restrict__ vals,
-                                                                   const float* __restrict__ idx,
-                                                                   long long* __restrict__ out,
-                                                                   int G, long long n) {
-    const long long i = (long long)blockIdx.x * SH_NT + threadIdx.x;
-    if (i >= n) return;
-    float best = vals[i];
-    float bi = idx[i];
-    for (int g = 1; g < G; ++g) {
-        const float v = vals[(long long)g * n + i];
-        if (v > best) { best = v; bi = idx[(long long)g * n + i]; }
-    }
-    out[i] = (long long)bi;
+template <int DL, int T>
+static void launch_stats(const float* x, const float* d, float* stats, int B, int HW, int off, cudaStream_t st) {
+    constexpr int PIX = SH_NT / T;
+    dim3 grid((HW + PIX - 1) / PIX, B);
+    shard_stats_kernel<DL, T><<<grid, SH_NT, 0, st>>>(x, d, stats, B, HW, off);
 }
 
 }  // namespace dpv
 
-extern "C" int dpv_shard_max(const float* x, float* local_max, float* local_argmax, int B, int D,
-                             int HW, int plane_offset, void* stream) {
+extern "C" int dpv_shard_stats(const float* x, const float* d_local, float* stats, int B, int D, int HW,
+                               int plane_offset, void* stream) {
     using namespace dpv;
-    DPV_CHECK_ARG(x && local_max && B > 0 && D > 0 && HW > 0);
-    dim3 grid((HW + SH_NT - 1) / SH_NT, B);
-    shard_max_kernel<<<grid, SH_NT, 0, (cudaStream_t)stream>>>(x, local_max, local_argmax, D, HW,
-                                                               plane_offset);
+    DPV_CHECK_ARG(x && d_local && stats && B > 0 && D > 0 && HW > 0 && plane_offset >= 0);
+    if (B > 65535) return DPV_E_UNSUPP;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (D) {
+        case 8: launch_stats<8, 1>(x, d_local, stats, B, HW, plane_offset, st); break;
+        case 16: launch_stats<16, 1>(x, d_local, stats, B, HW, plane_offset, st); break;
+        case 32: launch_stats<32, 1>(x, d_local, stats, B, HW, plane_offset, st); break;
+        case 64: launch_stats<64, 2>(x, d_local, stats, B, HW, plane_offset, st); break;
+        case 128: launch_stats<128, 4>(x, d_local, stats, B, HW, plane_offset, st); break;
+        default: {
+            dim3 grid((HW + SH_NT - 1) / SH_NT, B);
+            shard_stats_generic_kernel<<<grid, SH_NT, 0, st>>>(x, d_local, stats, B, D, HW, plane_offset);
+        }
+    }
     DPV_LAUNCH_END();
     return 0;
 }
 
-extern "C" int dpv_shard_sums(const float* x, const float* d_local, const float* global_max,
-                              float* sums, int B, int D, int HW, void* stream) {
+extern "C" int dpv_shard_merge_finish(const float* x, const float* gathered, float* logp, float* depth,
+                                      float* variance, int64_t* argmax, int G, int B, int D, int HW,
+                                      void* stream) {
     using namespace dpv;
-    DPV_CHECK_ARG(x && d_local && global_max && sums && B > 0 && D > 0 && HW > 0);
+    DPV_CHECK_ARG(x && gathered && G > 0 && B > 0 && D > 0 && HW > 0);
+    if (B > 65535) return DPV_E_UNSUPP;
     dim3 grid((HW + SH_NT - 1) / SH_NT, B);
-    shard_sums_kernel<<<grid, SH_NT, 0, (cudaStream_t)stream>>>(x, d_local, global_max, sums, B, D, HW);
-    DPV_LAUNCH_END();
-    return 0;
-}
-
-extern "C" int dpv_shard_central(const float* x, const float* d_local, const float* global_max,
-                                 const float* global_sums, float* central, int B, int D, int HW,
-                                 void* stream) {
-    using namespace dpv;
-    DPV_CHECK_ARG(x && d_local && global_max && global_sums && central && B > 0 && D > 0 && HW > 0);
-    dim3 grid((HW + SH_NT - 1) / SH_NT, B);
-    shard_central_kernel<<<grid, SH_NT, 0, (cudaStream_t)stream>>>(x, d_local, global_max,
-                                                                   global_sums, central, B, D, HW);
-    DPV_LAUNCH_END();
-    return 0;
-}
-
-extern "C" int dpv_shard_finish(const float* x, const float* global_max, const float* global_sums,
-                                const float* global_central, float* logp, float* depth,
-                                float* variance, int B, int D, int HW, void* stream) {
-    using namespace dpv;
-    DPV_CHECK_ARG(x && global_max && global_sums && B > 0 && D > 0 && HW > 0);
-    dim3 grid((HW + SH_NT - 1) / SH_NT, B);
-    shard_finish_kernel<<<grid, SH_NT, 0, (cudaStream_t)stream>>>(
-        x, global_max, global_sums, global_central, logp, depth, variance, B, D, HW);
-    DPV_LAUNCH_END();
-    return 0;
-}
-
-extern "C" int dpv_shard_argmax_merge(const float* vals, const float* idx, int64_t* out, int G,
-                                      int64_t n, void* stream) {
-    using namespace dpv;
-    DPV_CHECK_ARG(vals && idx && out && G > 0 && n > 0);
-    shard_argmax_merge_kernel<<<(unsigned)((n + SH_NT - 1) / SH_NT), SH_NT, 0, (cudaStream_t)stream>>>(
-        vals, idx, (long long*)out, G, n);
+    shard_merge_finish_kernel<<<grid, SH_NT, 0, (cudaStream_t)stream>>>(x, gathered, logp, depth, variance,
+                                                                         (long long*)argmax, G, B, D, HW);
     DPV_LAUNCH_END();
     return 0;
 }

@@ -9,11 +9,13 @@ Two partitionings:
   (kittiloader/batch_scheduler.py:345-352).  There is no data-path collective.
 
 * depth planes (large D) -- rank r owns planes [lo, hi) of a cost volume whose D planes do not
-  fit or are too slow on one GPU.  Not in the reference.  The soft-max over D then needs one
-  exchange: per-pixel max (all-reduce MAX), per-pixel sums (all-reduce SUM) and, for the variance,
-  the central second moment (all-reduce SUM); the MAP bin is merged first-maximum-wins from the
-  gathered (value, index) candidates.  Payload: 4-8 bytes per pixel per collective, i.e. latency
-  bound on NVLink; the collectives are NCCL calls enqueued on the kernels' stream.
+  fit or are too slow on one GPU.  Not in the reference.  The soft-max over D then needs ONE
+  exchange: every rank reduces its planes to five numbers per pixel (local max, sum of exponentials,
+  local mean, local central second moment, first local arg-max: dpv_shard_stats, one pass with the
+  planes in registers), the ranks all-gather those 20 bytes per pixel (one NCCL collective over
+  NVLink, enqueued on the kernels' stream), and every rank merges the G records with the
+  online-soft-max / pairwise-variance rules while it writes its planes of the log-softmax
+  (dpv_shard_merge_finish).  Two reads and one write of the local slice, one collective.
 
 The local passes are the dpv_shard_* kernels of libdpv_sm100a.so.  `PlaneShardedHead` takes the
 object that provides them as `local` so that the exchange protocol can be exercised by the CPU
@@ -74,6 +76,8 @@ def max_over_ranks(value, group=None, device=None):
 class CudaShardKernels:
     """The dpv_shard_* entry points (include/dpv_b200.h) on the current torch stream."""
 
+    NSTAT = 5
+
     def __init__(self):
         self.lib = _lib.load()
 
@@ -81,45 +85,25 @@ class CudaShardKernels:
     def _st():
         return torch.cuda.current_stream().cuda_stream
 
-    def local_max(self, x, lo, want_argmax):
+    def local_stats(self, x, d_local, lo, out=None):
+        """x [B, D_local, HW] -> stats [5, B*HW]: local max, sum exp, local mean, local M2, first arg-max."""
         ops._need(x, "x")
         B, Dl, HW = x.shape
-        m = torch.empty((B, HW), device=x.device, dtype=torch.float32)
-        am = torch.empty((B, HW), device=x.device, dtype=torch.float32) if want_argmax else None
-        _lib.check(self.lib.dpv_shard_max(x.data_ptr(), m.data_ptr(), ops._p(am), B, Dl, HW, int(lo),
-                                          self._st()))
-        return m, am
+        st = out if out is not None else torch.empty((self.NSTAT, B * HW), device=x.device, dtype=torch.float32)
+        _lib.check(self.lib.dpv_shard_stats(x.data_ptr(), d_local.data_ptr(), st.data_ptr(), B, Dl, HW, int(lo),
+                                            self._st()))
+        return st
 
-    def local_sums(self, x, d_local, gmax):
+    def merge_finish(self, x, gathered, want_logp, want_var, want_argmax):
+        """gathered [G, 5, B*HW] (ranks in plane order) -> (logp of the local planes, depth, variance, argmax)."""
         B, Dl, HW = x.shape
-        s = torch.empty((2, B, HW), device=x.device, dtype=torch.float32)
-        _lib.check(self.lib.dpv_shard_sums(x.data_ptr(), d_local.data_ptr(), gmax.data_ptr(),
-                                           s.data_ptr(), B, Dl, HW, self._st()))
-        return s
-
-    def local_central(self, x, d_local, gmax, gsums):
-        B, Dl, HW = x.shape
-        c = torch.empty((B, HW), device=x.device, dtype=torch.float32)
-        _lib.check(self.lib.dpv_shard_central(x.data_ptr(), d_local.data_ptr(), gmax.data_ptr(),
-                                              gsums.data_ptr(), c.data_ptr(), B, Dl, HW, self._st()))
-        return c
-
-    def finish(self, x, gmax, gsums, gcentral, want_logp, want_depth):
-        B, Dl, HW = x.shape
+        G = gathered.shape[0]
+        e = lambda dt=torch.float32: torch.empty((B, HW), device=x.device, dtype=dt)
         logp = torch.empty_like(x) if want_logp else None
-        depth = torch.empty((B, HW), device=x.device, dtype=torch.float32) if want_depth else None
-        var = torch.empty((B, HW), device=x.device, dtype=torch.float32) if gcentral is not None else None
-        _lib.check(self.lib.dpv_shard_finish(x.data_ptr(), gmax.data_ptr(), gsums.data_ptr(),
-                                             ops._p(gcentral), ops._p(logp), ops._p(depth), ops._p(var),
-                                             B, Dl, HW, self._st()))
-        return logp, depth, var
-
-    def argmax_merge(self, vals, idx):
-        G, n = vals.shape[0], vals[0].numel()
-        out = torch.empty((n,), device=vals.device, dtype=torch.int64)
-        _lib.check(self.lib.dpv_shard_argmax_merge(vals.data_ptr(), idx.data_ptr(), out.data_ptr(),
-                                                   G, n, self._st()))
-        return out
+        depth, var, am = e(), (e() if want_var else None), (e(torch.int64) if want_argmax else None)
+        _lib.check(self.lib.dpv_shard_merge_finish(x.data_ptr(), gathered.data_ptr(), ops._p(logp), depth.data_ptr(),
+                                                   ops._p(var), ops._p(am), G, B, Dl, HW, self._st()))
+        return logp, depth, var, am
 
 
 class PlaneShardedHead:
@@ -140,6 +124,7 @@ class PlaneShardedHead:
         self.D = int(D)
         self.lo, self.hi = plane_range(self.D, self.rank, self.world)
         self.local = local if local is not None else CudaShardKernels()
+        self._buf = None        # (key, stats, gathered): reused call after call (no allocation on the path)
 
     def _local_bins(self, d_candi, device):
         """This rank's slice of the (global) bin depths on the device; uploaded once per bin vector."""
@@ -152,47 +137,32 @@ class PlaneShardedHead:
         self._bins_cache = (key, d_all, t)
         return t
 
-    def _all_reduce(self, t, op):
-        if self.world > 1:
-            self.dist.all_reduce(t, op=op, group=self.group)
-        return t
-
     def __call__(self, x_local, d_candi, variance=True, argmax=True, logp=True):
-        dist = self.dist
         B, Dl, H, W = x_local.shape
         if Dl != self.hi - self.lo:
             raise ValueError("rank %d owns %d planes, got %d" % (self.rank, self.hi - self.lo, Dl))
         x = x_local.contiguous().reshape(B, Dl, H * W)
         d_local = self._local_bins(d_candi, x.device)
-        m, am = self.local.local_max(x, self.lo, argmax)
-        out = {}
-        if argmax:
-            if self.world > 1:
-                # one all-gather of (max, arg-max) per rank serves both the arg-max merge and the global
-                # maximum (no separate MAX all-reduce)
-                cand = torch.stack([m, am]).contiguous()
-                gathered = [torch.empty_like(cand) for _ in range(self.world)]
-                dist.all_gather(gathered, cand, group=self.group)
-                vals = torch.stack([g[0] for g in gathered]).contiguous()
-                idx = torch.stack([g[1] for g in gathered]).contiguous()
-                gmax = vals.max(dim=0).values.contiguous()
-            else:
-                vals, idx = m.unsqueeze(0).contiguous(), am.unsqueeze(0).contiguous()
-                gmax = m
-            out["argmax"] = self.local.argmax_merge(vals, idx).reshape(B, H, W)
+        n = B * H * W
+        key = (n, str(x.device))
+        if self._buf is None or self._buf[0] != key:
+            self._buf = (key, torch.empty((5, n), device=x.device, dtype=torch.float32),
+                         torch.empty((self.world, 5, n), device=x.device, dtype=torch.float32))
+        _, stats, gathered = self._buf
+        stats = self.local.local_stats(x, d_local, self.lo, out=stats)
+        if self.world > 1:
+            # the one exchange (output = the ranks' records concatenated along dim 0, in rank = plane order)
+            self.dist.all_gather_into_tensor(gathered.view(self.world * 5, n), stats, group=self.group)
         else:
-            gmax = self._all_reduce(m.clone(), dist.ReduceOp.MAX)
-        gsums = self._all_reduce(self.local.local_sums(x, d_local, gmax), dist.ReduceOp.SUM)
-        gcentral = None
-        if variance:
-            gcentral = self._all_reduce(self.local.local_central(x, d_local, gmax, gsums),
-                                        dist.ReduceOp.SUM)
-        lp, depth, var = self.local.finish(x, gmax, gsums, gcentral, logp, True)
+            gathered = stats.unsqueeze(0)
+        lp, depth, var, am = self.local.merge_finish(x, gathered, logp, variance, argmax)
+        out = {"depth": depth.reshape(B, H, W)}
         if logp:
             out["logp"] = lp.reshape(B, Dl, H, W)
-        out["depth"] = depth.reshape(B, H, W)
         if variance:
             out["variance"] = var.reshape(B, H, W)
+        if argmax:
+            out["argmax"] = am.reshape(B, H, W)
         return out
 
 

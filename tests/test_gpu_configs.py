@@ -187,27 +187,23 @@ def test_upsample_batch32_full_size_properties(dpv):
 
 # ----------------------------------------------------------------- configs[4]: large D, plane shards
 def _merge_plane_shards(sh, x, d, world):
-    """PlaneShardedHead's exchange steps with the collectives done by hand on one device."""
+    """PlaneShardedHead's two kernels with the all-gather done by hand on one device."""
     k = sh.CudaShardKernels()
     B, D, H, W = x.shape
-    xs, ds, los = [], [], []
+    xs, stats = [], []
     for r in range(world):
         lo, hi = sh.plane_range(D, r, world)
         xs.append(x[:, lo:hi].contiguous().reshape(B, hi - lo, H * W))
-        ds.append(cu(np.asarray(d, np.float64).astype(np.float32)[lo:hi]))
-        los.append(lo)
-    mx = [k.local_max(xs[r], los[r], True) for r in range(world)]
-    gmax = torch.stack([m for m, _ in mx]).max(0).values.contiguous()                    # all-reduce MAX
-    amax = k.argmax_merge(torch.stack([m for m, _ in mx]).contiguous(),
-                          torch.stack([a for _, a in mx]).contiguous()).reshape(B, H, W)  # all-gather
-    gsums = torch.stack([k.local_sums(xs[r], ds[r], gmax) for r in range(world)]).sum(0).contiguous()
-    gcen = torch.stack([k.local_central(xs[r], ds[r], gmax, gsums) for r in range(world)]).sum(0).contiguous()
-    outs = [k.finish(xs[r], gmax, gsums, gcen, True, True) for r in range(world)]
+        stats.append(k.local_stats(xs[r], cu(np.asarray(d, np.float64).astype(np.float32)[lo:hi]), lo))
+    gathered = torch.stack(stats).contiguous()                                           # all-gather
+    outs = [k.merge_finish(xs[r], gathered, True, True, True) for r in range(world)]
+    for o in outs[1:]:      # the per-pixel products come out replicated, bit for bit
+        assert torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2]) and torch.equal(o[3], outs[0][3])
     logp = torch.cat([o[0].reshape(B, -1, H, W) for o in outs], 1)
-    return logp, outs[0][1].reshape(B, H, W), outs[0][2].reshape(B, H, W), amax
+    return logp, outs[0][1].reshape(B, H, W), outs[0][2].reshape(B, H, W), outs[0][3].reshape(B, H, W)
 
 
-@pytest.mark.parametrize("D,world", [(128, 2), (128, 8), (256, 4)])
+@pytest.mark.parametrize("D,world", [(128, 2), (128, 8), (256, 4), (256, 2), (256, 8), (100, 3)])
 def test_large_d_plane_sharded_head_equals_unsharded(dpv, D, world):
     sh = importlib.import_module("probabilistic-depth_b200.sharding")
     B, H, W = 1, 48, 160

@@ -26,37 +26,34 @@ if ROOT not in sys.path:
 class TorchShardStandIn:
     """What csrc/shard.cu computes, in torch CPU ops (test stand-in for CudaShardKernels)."""
 
-    def local_max(self, x, lo, want_argmax):
-        m, am = x.max(dim=1)
-        # first maximum wins inside the shard, as shard_max_kernel's strict '>' does
-        first = (x == m.unsqueeze(1)).float().argmax(dim=1)
-        return m.contiguous(), (first + lo).float().contiguous() if want_argmax else None
+    def local_stats(self, x, d_local, lo, out=None):
+        B, Dl, HW = x.shape
+        m = x.max(dim=1).values
+        first = (x == m.unsqueeze(1)).float().argmax(dim=1)          # first maximum wins inside the shard
+        e = torch.exp(x - m.unsqueeze(1))
+        s0 = e.sum(1)
+        mu = (e * d_local.view(1, -1, 1)).sum(1) / s0
+        m2 = (e * (d_local.view(1, -1, 1) - mu.unsqueeze(1)) ** 2).sum(1)
+        st = torch.stack([m, s0, mu, m2, (first + lo).float()]).reshape(5, B * HW).contiguous()
+        if out is not None:
+            out.copy_(st)
+            return out
+        return st
 
-    def local_sums(self, x, d_local, gmax):
-        e = torch.exp(x - gmax.unsqueeze(1))
-        return torch.stack([e.sum(1), (e * d_local.view(1, -1, 1)).sum(1)]).contiguous()
-
-    def local_central(self, x, d_local, gmax, gsums):
-        e = torch.exp(x - gmax.unsqueeze(1))
-        mean = gsums[1] / gsums[0]
-        dd = d_local.view(1, -1, 1) - mean.unsqueeze(1)
-        return (dd * dd * e).sum(1).contiguous()
-
-    def finish(self, x, gmax, gsums, gcentral, want_logp, want_depth):
-        ls = torch.log(gsums[0])
-        logp = (x - gmax.unsqueeze(1)) - ls.unsqueeze(1) if want_logp else None
-        depth = gsums[1] / gsums[0] if want_depth else None
-        var = gcentral / gsums[0] if gcentral is not None else None
-        return logp, depth, var
-
-    def argmax_merge(self, vals, idx):
-        best, bi = vals[0].reshape(-1).clone(), idx[0].reshape(-1).clone()
-        for g in range(1, vals.shape[0]):
-            v, i = vals[g].reshape(-1), idx[g].reshape(-1)
-            take = v > best
-            best = torch.where(take, v, best)
-            bi = torch.where(take, i, bi)
-        return bi.long()
+    def merge_finish(self, x, gathered, want_logp, want_var, want_argmax):
+        B, Dl, HW = x.shape
+        g = gathered.reshape(gathered.shape[0], 5, B, HW)
+        m, s0, mu, m2, am = g[:, 0], g[:, 1], g[:, 2], g[:, 3], g[:, 4]
+        M = m.max(dim=0).values
+        sc = torch.exp(m - M.unsqueeze(0))
+        w = s0 * sc
+        S = w.sum(0)
+        mean = (w * mu).sum(0) / S
+        var = ((m2 * sc + w * (mu - mean.unsqueeze(0)) ** 2).sum(0) / S) if want_var else None
+        first_rank = (m == M.unsqueeze(0)).float().argmax(dim=0)     # first rank attaining the maximum
+        amax = torch.gather(am, 0, first_rank.unsqueeze(0))[0].long() if want_argmax else None
+        logp = (x - M.unsqueeze(1)) - torch.log(S).unsqueeze(1) if want_logp else None
+        return logp, mean, var, amax
 
 
 def _free_port():

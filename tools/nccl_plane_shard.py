@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """configs[4] over real NCCL: depth-plane-sharded sweep + soft-max statistics all-reduce, one rank per GPU.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/nccl_plane_shard.py
-Every rank owns D/N planes of the cost volume (features replicated), PlaneShardedHead exchanges the per-pixel
-max / sums / central moment (NCCL all-reduce on the kernels' stream); each rank then checks its planes of the
-log-softmax and the replicated E[d] / Var / arg-max against the unsharded computation on its own GPU."""
+Every rank owns D/N planes of the cost volume (features replicated), PlaneShardedHead reduces them to five
+statistics per pixel, all-gathers those (ONE NCCL collective) and merges; each rank then checks its planes of the
+log-softmax and the replicated E[d] / Var / arg-max against the unsharded computation on its own GPU, and times
+the sharded head against the unsharded dpv_head on the whole volume."""
 import importlib, os, sys
 import numpy as np, torch
 import torch.distributed as dist
@@ -28,11 +29,23 @@ for D, h, w in ((128, 96, 320), (256, 384, 1280)):
     cost_local, (lo, hi) = sh.plane_sharded_sweep(feats[:, -1], feats[:, :-1], poses[:, :-1], K, rays, d, 10.0, rank, world)
     head = sh.PlaneShardedHead(D)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    res = head(cost_local, d)                      # warm-up (communicator set-up)
+    for _ in range(3):
+        res = head(cost_local, d)                  # warm-up (communicator set-up)
     torch.cuda.synchronize(); dist.barrier()
-    t0.record(); res = head(cost_local, d); t1.record(); torch.cuda.synchronize()
+    NIT = 20
+    t0.record()
+    for _ in range(NIT):
+        res = head(cost_local, d)
+    t1.record(); torch.cuda.synchronize()
+    sharded_ms = t0.elapsed_time(t1) / NIT
     full = dpv.ops.sweep_cost_volume(feats[:, -1], feats[:, :-1], poses[:, :-1], K, rays, d, 10.0)
     one = dpv.ops.head(full, d, logp=True, depth=True, variance=True, argmax=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(NIT):
+        one = dpv.ops.head(full, d, logp=True, depth=True, variance=True, argmax=True)
+    t1.record(); torch.cuda.synchronize()
+    single_ms = t0.elapsed_time(t1) / NIT
     def err(a, b): return float(((a - b).abs() / b.abs().clamp_min(1.0)).max())
     e = dict(logp=err(res["logp"], one["logp"][:, lo:hi]), depth=err(res["depth"], one["depth"]),
              var=err(res["variance"], one["variance"]), argmax_equal=bool(torch.equal(res["argmax"], one["argmax"])))
@@ -43,8 +56,8 @@ for D, h, w in ((128, 96, 320), (256, 384, 1280)):
         clear = (top2[:, 0] - top2[:, 1]) > 1e-4
         good = good and bool(torch.equal(res["argmax"][clear], one["argmax"][clear]))
     ok = ok and good
-    print("rank %d/%d D=%d %dx%d planes [%d,%d): %s  sharded head %.3f ms  %s" %
-          (rank, world, D, h, w, lo, hi, e, t0.elapsed_time(t1), "OK" if good else "MISMATCH"), file=out, flush=True)
+    print("rank %d/%d D=%d %dx%d planes [%d,%d): %s  sharded head %.3f ms  unsharded dpv_head on one GPU %.3f ms  %s" %
+          (rank, world, D, h, w, lo, hi, e, sharded_ms, single_ms, "OK" if good else "MISMATCH"), file=out, flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
