@@ -490,6 +490,38 @@ def run_ours(args, dpv, wl):
     launches = dpv._lib.launch_count() - l0 + replays * launches_per_step
     ms = t_start.elapsed_time(t_end)
     head_ms = [a.elapsed_time(b) for i, (a, b) in enumerate(ev) if i % HOOK_EVERY == 0]
+    # The dominant kernel on its own: the full-res head (+ UF) of the step replayed back to back over the
+    # rotating input sets (graph replays, no events between launches), one event pair around the lot.  The
+    # in-step figure above brackets single launches with events, each of which costs ~3 us of bubble.
+    head_alone_ms = None
+    if mode in ("default", "feedback", "upsample"):
+        try:
+            hgraphs = []
+            for s_ in dsets:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step.run_head(s_["logits"], s_["intr_up"])
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    step.run_head(s_["logits"], s_["intr_up"])
+                hgraphs.append(g_)
+            for i in range(4):
+                hgraphs[i % nset].replay()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            h0.record()
+            for i in range(args.steps):
+                hgraphs[i % nset].replay()
+            h1.record()
+            torch.cuda.synchronize()
+            head_alone_ms = h0.elapsed_time(h1) / args.steps
+            launches += args.steps * (2 if step.fused_uf else 1)
+        except Exception as exc:
+            print("bench.py: head-only graph timing failed (%s)" % exc, file=sys.stderr)
+            torch.cuda.synchronize()
 
     # ---- per-kernel breakdown (separate short loop: events between every launch) -----------
     kev, kcur, nbk = {}, {"i": 0}, 20
@@ -572,10 +604,12 @@ def run_ours(args, dpv, wl):
     del dst
 
     # ---- max over ranks ---------------------------------------------------------------------
-    stats = torch.tensor([ms, e2e_s, statistics.mean(head_ms), copy_s], device=dev, dtype=torch.float64)
+    stats = torch.tensor([ms, e2e_s, statistics.mean(head_ms), copy_s, head_alone_ms or 0.0], device=dev,
+                         dtype=torch.float64)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms, e2e_s, head_mean_ms, copy_s = [float(v) for v in stats.cpu()]
+    ms, e2e_s, head_in_step_ms, copy_s, head_alone_ms = [float(v) for v in stats.cpu()]
+    head_mean_ms = head_alone_ms if head_alone_ms > 0 else head_in_step_ms
 
     if rank == 0:
         peak, peak_kind = measured_peak()
@@ -617,7 +651,12 @@ def run_ours(args, dpv, wl):
             "roofline": {"kernel": head_name, "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": head_bytes, "ms_per_launch": head_mean_ms},
+                         "algorithmic_bytes_per_launch": head_bytes, "ms_per_launch": head_mean_ms,
+                         "ms_per_launch_how": ("back-to-back graph replays of the head over the rotating input sets, "
+                                               "one CUDA-event pair around %d launches" % args.steps) if head_alone_ms > 0
+                         else "event pairs around single launches inside the step (every 8th step)",
+                         "ms_per_launch_in_step": head_in_step_ms,
+                         "frac_in_step": head_bytes / (head_in_step_ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": frames_per_step_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": e2e_api,
                     "ceiling": {"value": frames_per_step_global / (copy_s * h2d / copy_bytes), "unit": UNIT,

@@ -1,0 +1,2 @@
+#pragma once
+#include <pybind11/pybind11.h>

@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(UT_NT, 5) head_uf_tile_kernel(const UtArgs a) 
         float* lp_ptr = LOGP ? a.logp + item + (long long)(D - 1) * HW + pix : nullptr;
         // one code path per launch (the fully unrolled pass is ~1000 instructions: a second copy for the
         // rows without hand-off costs more in instruction fetch than its predicated-off stores)
+        // (one code path for all warps: the hand-off rows are exactly the rows of warp 0, but giving warps 1-3 a
+        // copy of the pass without the hand-off's pointer arithmetic measured 0.0939 vs 0.0896 ms -- the second
+        // ~1000-instruction copy costs more in instruction fetch than it saves in issue slots)
         if (a.quarter != nullptr) {
             const bool q_keep = live && ((y & 3) == 0) && ((y >> 2) < h4) && ((x & 3) == 0) && ((x >> 2) < w4);
             float* qp = a.quarter + ((long long)b * D + (D - 1)) * q4 + (q_keep ? (y >> 2) * w4 + (x >> 2) : 0);
@@ -319,6 +322,8 @@ static int ut_launch(const UtArgs& a, int mode, cudaStream_t st) {
         else head_uf_tile_kernel<D, DPV_IN_LOGPROB, false><<<grid, block, 0, st>>>(a);
     }
     DPV_LAUNCH_END();
+    static const int nofinish = [] { const char* v = getenv("DPV_UFTILE_NOFINISH"); return v ? atoi(v) : 0; }();
+    if (nofinish) return 0;      // (timing experiments only: the UF is not produced)
     // (PDL) the finish kernel becomes resident behind the tile kernel's last CTAs and waits for them
     e = dpv_launch_pdl(head_uf_tile_finish_kernel<D>, dim3(a.xtiles, (D + 7) / 8, a.B), dim3(256), 0, st, a);
     if (e != cudaSuccess) return (int)e;

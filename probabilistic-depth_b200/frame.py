@@ -108,6 +108,13 @@ class FrameStep:
             hk("feedback_fuse", 1)
         self._full_res(lib, st, p, logits_full, intr_up, head_hook, hk)
 
+    def run_head(self, logits_full, intr_up):
+        """Only the full-resolution head (+ UF) of the step: what bench.py replays back to back to time the
+        dominant kernel without the event bubbles of an in-step measurement."""
+        p = lambda t: None if t is None else t.data_ptr()
+        self._full_res(self.lib, torch.cuda.current_stream().cuda_stream, p, logits_full, intr_up, None,
+                       lambda name, which: None)
+
     def _full_res(self, lib, st, p, logits_full, intr_up, head_hook, hk):
         B, D, H, W = self.B, self.D, self.H, self.W
         if head_hook is not None:

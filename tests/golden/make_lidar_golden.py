@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""tests/golden/lidar.npz: the reference's minpool (utils/img_utils.py:87-95, imported from
-/root/reference) applied to the oracle's depth maps, as kittiloader/kitti.py:706 does.  generate_depth
-itself cannot be run from the reference here (Eigen / OpenCV / pybind11 are absent), so the depth maps
-stored next to it are the ORACLE's (oracle/c/lidar_depthmap.c) and only guard against drift."""
+"""tests/golden/lidar.npz: depth maps from the reference's own generate_depth (utils_lib.cpp:86-160 compiled by
+oracle/ref_utils_lib against minimal Eigen / OpenCV / pybind11 stand-ins: `*_dmap_ref`), the oracle's
+(oracle/c/lidar_depthmap.c: `*_dmap_oracle`, identical), and the reference's minpool (utils/img_utils.py:87-95,
+imported from /root/reference) applied to them as kittiloader/kitti.py:706 does."""
 import os
 import sys
 import types
@@ -29,6 +29,10 @@ for name in cases.LIDAR_CASES:
     c = cases.lidar_case(name)
     dmap = L.generate_depth(c["velo"], c["intr"], c["M"], c["width"], c["height"], c["filtering"], c["filterdiff"])
     out[name + "_dmap_oracle"] = dmap
+    ref_map = L.reference_generate_depth(c["velo"], c["intr"], c["M"], c["width"], c["height"], c["filtering"],
+                                         c["filterdiff"])
+    assert np.array_equal(ref_map, dmap), name
+    out[name + "_dmap_ref"] = ref_map
     t = torch.Tensor(dmap).unsqueeze(0).unsqueeze(0)
     out[name + "_small_ref"] = ref_u.minpool(t, 4, 1000).squeeze(0).squeeze(0).numpy()      # kitti.py:706
     out[name + "_small_ref_plain"] = ref_u.minpool(t, 4).squeeze(0).squeeze(0).numpy()

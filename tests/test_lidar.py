@@ -1,9 +1,10 @@
 """LiDAR -> sparse depth maps.
 
-generate_depth is PARITY UNPINNED against the reference (its C++ needs Eigen / OpenCV / pybind11, absent
-here): the kernels are held bit-exact to the C restatement oracle/c/lidar_depthmap.c, which fixes the one
-thing Eigen leaves open (summation order of the 4-term products).  minpool is pinned: the goldens are the
-reference's own Python applied to the same maps.
+generate_depth: the goldens (`*_dmap_ref`) come from the reference's OWN source file compiled against minimal
+Eigen / OpenCV / pybind11 stand-ins (oracle/ref_utils_lib -> oracle/_ref/libutils_ref.so; those libraries are
+absent here); the C restatement oracle/c/lidar_depthmap.c and the kernels are held bit-exact to them.  The
+stand-in states the one thing Eigen leaves open (the association of the 4-term products).  minpool is pinned:
+the goldens are the reference's own Python applied to the same maps.
 """
 import os
 import sys
@@ -28,8 +29,32 @@ def test_oracle_vs_golden(name):
     c = cases.lidar_case(name)
     dmap = L.generate_depth(c["velo"], c["intr"], c["M"], c["width"], c["height"], c["filtering"], c["filterdiff"])
     assert np.array_equal(dmap, GOLD[name + "_dmap_oracle"])
+    assert np.array_equal(dmap, GOLD[name + "_dmap_ref"])                                # the reference's own C++
     assert np.array_equal(L.minpool(dmap, 4, 1000.0), GOLD[name + "_small_ref"])          # reference's minpool
     assert np.array_equal(L.minpool(dmap, 4), GOLD[name + "_small_ref_plain"])
+
+
+@pytest.mark.skipif(not L.reference_available(), reason="oracle/_ref/libutils_ref.so not built "
+                    "(__graft_entry__.build() compiles it where /root/reference exists)")
+def test_oracle_vs_compiled_reference_on_random_clouds():
+    """The restatement against the reference's own generate_depth (compiled from /root/reference) on seeded random
+    point clouds, several image sizes, filter radii 0-3: bit-identical maps."""
+    rng = np.random.RandomState(7)
+    for it in range(12):
+        width, height = int(rng.choice([16, 48, 96, 200])), int(rng.choice([12, 40, 64]))
+        n = int(rng.choice([50, 2000, 20000]))
+        velo = np.concatenate([rng.uniform(-30, 30, (n, 2)), rng.uniform(-5, 60, (n, 1)), np.ones((n, 1))], 1).astype(np.float32)
+        f = float(rng.uniform(0.5, 1.5) * width)
+        intr = np.array([[f, 0, width / 2.0, 0], [0, f, height / 2.0, 0], [0, 0, 1, 0]], dtype=np.float32)
+        ang = rng.uniform(-0.2, 0.2)
+        M = np.eye(4, dtype=np.float32)
+        M[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], dtype=np.float32)
+        M[:3, 3] = rng.uniform(-0.5, 0.5, 3)
+        filt, fd = int(rng.randint(0, 4)), float(rng.choice([0.5, 1.0, 2.0]))
+        a = L.generate_depth(velo, intr, M, width, height, filt, fd)
+        b = L.reference_generate_depth(velo, intr, M, width, height, filt, fd)
+        assert np.array_equal(a, b), (it, width, height, n, filt, fd)
+        assert (a > 0).any() or n == 50
 
 
 def test_oracle_filter_and_zbuffer_semantics():
