@@ -1,21 +1,30 @@
 #!/bin/bash
-# One GPU round (dev tool): full -m gpu suite, smoke, the contract bench and the other workloads.  Outputs -> gpurun_out/
+# One GPU round (dev tool): full -m gpu suite, smoke, the contract bench (both arms), the other workloads,
+# per-kernel graph timings, ncu launch list + one --set full capture of the step, compute-sanitizer.
+# Outputs -> gpurun_out/   (copy what is to be kept into profiles/)
 O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=index,name,clocks.max.sm,power.limit --format=csv > $O/gpu.csv
-python -m pytest tests -q -m gpu 2>&1 | tail -15 > $O/pytest_gpu.log; tail -4 $O/pytest_gpu.log
+python -m pytest tests -q -m gpu 2>&1 | tail -15 > $O/pytest_gpu.log; tail -2 $O/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; tail -3 $O/bench_n1.err
 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"
 for w in feedback upsample stress large_d; do
   python bench.py --workload $w --steps 50 > $O/bench_$w.json 2> $O/bench_$w.err; echo "$w rc=$?"; tail -2 $O/bench_$w.err
 done
+python tools/bench_kernels.py --graph > $O/kernels_graph.log 2>&1; grep -v "^{" $O/kernels_graph.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/launches_bench.log 2>&1; echo "ncu launch list rc=$?"
+N=3 ncu --set full --clock-control none --import-source on -k regex:"sweep_xcorr|sweep_smaps|head_uf_tile" -s 5 -c 4 \
+    -o $O/prof_step python tools/run_once.py > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
+compute-sanitizer --tool memcheck python tools/run_small_step.py > $O/sanitizer_memcheck.log 2>&1; tail -3 $O/sanitizer_memcheck.log
+compute-sanitizer --tool racecheck python tools/run_small_step.py > $O/sanitizer_racecheck.log 2>&1; tail -3 $O/sanitizer_racecheck.log
 python - <<'PY'
 import json
 for n in ("n1", "feedback", "upsample", "stress", "large_d"):
     try:
         d = json.loads(open("gpurun_out/bench_%s.json" % n).read())
-        print(n, "value %.0f  ms %.4f  roofline %.3f  frame_hbm %.3f  survey_hbm %.3f  e2e %.0f (%.2f of ceiling)  incumbent %s  cpu %s" % (
-            d["value"], d["ms_per_step"], d["roofline"]["frac"], d["config"]["frame_hbm_frac"], d["config"]["survey_hbm_frac"],
+        print(n, "value %.0f  ms %.4f  roofline %.3f (in step %.3f)  frame_hbm %.3f  survey_hbm %.3f  e2e %.0f (%.2f of ceiling)  incumbent %s  cpu %s" % (
+            d["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"].get("frac_in_step", 0), d["config"]["frame_hbm_frac"], d["config"]["survey_hbm_frac"],
             d["e2e"]["value"], d["e2e"]["frac_of_ceiling"], d.get("incumbent", {}).get("value"), d.get("cpu_baseline", {}).get("value")))
         print("   kernels", {k: round(v["ms"], 4) for k, v in d["kernels"].items()})
     except Exception as e:
