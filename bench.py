@@ -366,7 +366,7 @@ def run_ours(args, dpv, wl):
         raise SystemExit("bench.py: no CUDA device; the DPV path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    bound_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
+    bound_cpus = 0
     out = sys.stdout
     if world > 1:
         # NCCL prints its version / debug lines on file descriptor 1 when NCCL_DEBUG is set in the
@@ -539,6 +539,10 @@ def run_ours(args, dpv, wl):
         kernel_ms = {n: statistics.median(a.elapsed_time(b) for a, b in lst) for n, lst in kev.items()}
 
     # ---- end to end through the host-buffer API ----------------------------------------------
+    # (the pinned host buffers are first touched here: bind to the CPUs next to this GPU for this part only -- a
+    # narrow affinity mask during the device-timed loops above would make the host threads of the ranks compete)
+    affinity0 = os.sched_getaffinity(0)
+    bound_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     e2e_steps = max(4, min(args.steps, 30))
     pipe = None
     if mode == "default":
@@ -602,6 +606,10 @@ def run_ours(args, dpv, wl):
     if pipe is not None:
         pipe.close()
     del dst
+    try:
+        os.sched_setaffinity(0, affinity0)
+    except Exception:
+        pass
 
     # ---- max over ranks ---------------------------------------------------------------------
     stats = torch.tensor([ms, e2e_s, statistics.mean(head_ms), copy_s, head_alone_ms or 0.0], device=dev,

@@ -208,9 +208,18 @@ int dpv_correlation(const float* x1, const float* x2, float* out, int B, int C, 
  *                             first-maximum-wins arg-max) and writes logp = x - M - log S for the local planes;
  *                             depth / variance / argmax [B*HW] come out replicated on every rank.  Any of
  *                             logp / depth / variance / argmax may be null.
+ * Reduce-scatter form (pays from G > 2: both collectives move 20 B x pixels per rank, independent of G):
+ *   dpv_shard_stats with slice = ceil(B*HW / G): records slice-major, [G][5][slice]
+ *   all-to-all             -> recv [G][5][slice]: rank g's statistics of MY slice of the pixels
+ *   dpv_shard_merge_slice  -> merged [5][slice]: M, log S, mean, variance, arg-max of my pixels
+ *   all-gather             -> all [G][5][slice]: the merged record of every pixel
+ *   dpv_shard_finish       -> logp of the local planes, depth / variance / argmax replicated
  */
 int dpv_shard_stats(const float* x, const float* d_local, float* stats, int B, int D, int HW,
-                    int plane_offset, void* stream);
+                    int plane_offset, int slice, void* stream);
+int dpv_shard_merge_slice(const float* recv, float* merged, int G, int slice, void* stream);
+int dpv_shard_finish(const float* x, const float* all, float* logp, float* depth, float* variance,
+                     int64_t* argmax, int B, int D, int HW, int slice, void* stream);
 int dpv_shard_merge_finish(const float* x, const float* gathered, float* logp, float* depth,
                            float* variance, int64_t* argmax, int G, int B, int D, int HW, void* stream);
 

@@ -34,7 +34,9 @@ PROTOTYPES = {
     "dpv_uf_fused_tables": (_c_i, [_c_fp] * 4 + [_c_i] * 2 + [_c_fp] * 2),
     "dpv_head_ufield": (_c_i, [_c_fp] * 13 + [_c_i] * 4 + [_c_i64, _c_i] + [_c_f] * 5 + [_c_fp]),
     "dpv_correlation": (_c_i, [_c_fp] * 3 + [_c_i] * 5 + [_c_fp]),
-    "dpv_shard_stats": (_c_i, [_c_fp] * 3 + [_c_i] * 4 + [_c_fp]),
+    "dpv_shard_stats": (_c_i, [_c_fp] * 3 + [_c_i] * 5 + [_c_fp]),
+    "dpv_shard_merge_slice": (_c_i, [_c_fp] * 2 + [_c_i] * 2 + [_c_fp]),
+    "dpv_shard_finish": (_c_i, [_c_fp] * 6 + [_c_i] * 4 + [_c_fp]),
     "dpv_shard_merge_finish": (_c_i, [_c_fp] * 6 + [_c_i] * 4 + [_c_fp]),
     "dpv_depth_errors_workspace_doubles": (_c_i64, [_c_i] * 3),
     "dpv_depth_errors": (_c_i, [_c_fp] * 3 + [_c_f, _c_i] + [_c_fp] * 3 + [_c_i] * 3 + [_c_fp]),

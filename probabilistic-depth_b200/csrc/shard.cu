@@ -15,6 +15,11 @@
 //   written: logp = x - M - log S.
 // Two reads and one write of the local slice (the first version read it four times and used three
 // collectives: 3 ms per call at world 2; profiles/r01f_nccl_plane_shard.txt).  HBM-bound.
+// The all-gather moves 20 B x pixels x G per rank, which at world 8 is more than the local slice itself.  For
+// G > 2 the exchange therefore has the reduce-scatter shape: shard_stats writes slice-major records, an
+// all-to-all hands rank g the G records of ITS 1/G of the pixels, shard_merge_slice merges them, an all-gather
+// replicates the merged records (20 B x pixels per rank in each of the two collectives, independent of G), and
+// shard_finish writes the planes.
 #include "dpv_common.cuh"
 
 namespace dpv {
@@ -42,11 +47,19 @@ __device__ __forceinline__ int sh_group_min(int v) {
 }
 
 // DL local planes, T lanes per pixel, DL / T planes per lane in registers: the slice is read once.
+// Where statistic `s` of pixel `pix` (of n) lives: five planes [5][n] (slice == 0), or slice-major
+// [n / slice][5][slice] -- the layout an all-to-all wants: block g is what rank g merges.
+__device__ __forceinline__ long long sh_stat_index(long long pix, int s, long long n, int slice) {
+    if (slice == 0) return (long long)s * n + pix;
+    const long long g = pix / slice;
+    return (g * SH_NSTAT + s) * slice + (pix - g * slice);
+}
+
 template <int DL, int T>
 __global__ void __launch_bounds__(SH_NT) shard_stats_kernel(const float* __restrict__ x,
                                                             const float* __restrict__ d,
                                                             float* __restrict__ stats, int B, int HW,
-                                                            int k_offset) {
+                                                            int k_offset, int slice) {
     constexpr int DT = DL / T, PIX = SH_NT / T;
     __shared__ float d_s[DL];
     for (int k = threadIdx.x; k < DL; k += SH_NT) d_s[k] = __ldg(d + k);
@@ -90,8 +103,9 @@ __global__ void __launch_bounds__(SH_NT) shard_stats_kernel(const float* __restr
     m2 = sh_group_sum<T>(m2);
     if (live && r == 0) {
         const long long n = (long long)B * HW, pix = (long long)b * HW + q;
-        stats[pix] = m; stats[n + pix] = s0; stats[2 * n + pix] = mu; stats[3 * n + pix] = m2;
-        stats[4 * n + pix] = (float)(first + k_offset);
+        stats[sh_stat_index(pix, 0, n, slice)] = m; stats[sh_stat_index(pix, 1, n, slice)] = s0;
+        stats[sh_stat_index(pix, 2, n, slice)] = mu; stats[sh_stat_index(pix, 3, n, slice)] = m2;
+        stats[sh_stat_index(pix, 4, n, slice)] = (float)(first + k_offset);
     }
 }
 
@@ -99,7 +113,7 @@ __global__ void __launch_bounds__(SH_NT) shard_stats_kernel(const float* __restr
 __global__ void __launch_bounds__(SH_NT) shard_stats_generic_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ d,
                                                                     float* __restrict__ stats, int B, int D,
-                                                                    int HW, int k_offset) {
+                                                                    int HW, int k_offset, int slice) {
     const int b = blockIdx.y;
     const int q = blockIdx.x * SH_NT + threadIdx.x;
     if (q >= HW) return;
@@ -126,8 +140,83 @@ __global__ void __launch_bounds__(SH_NT) shard_stats_generic_kernel(const float*
         m2 = fmaf(c * c, e, m2);
     }
     const long long n = (long long)B * HW, pix = (long long)b * HW + q;
-    stats[pix] = m; stats[n + pix] = s0; stats[2 * n + pix] = mu; stats[3 * n + pix] = m2;
-    stats[4 * n + pix] = (float)(first + k_offset);
+    stats[sh_stat_index(pix, 0, n, slice)] = m; stats[sh_stat_index(pix, 1, n, slice)] = s0;
+    stats[sh_stat_index(pix, 2, n, slice)] = mu; stats[sh_stat_index(pix, 3, n, slice)] = m2;
+    stats[sh_stat_index(pix, 4, n, slice)] = (float)(first + k_offset);
+}
+
+// The merge of G records of one pixel (ranks in plane order): online-soft-max weights, pairwise variance rule,
+// first rank attaining the maximum wins the arg-max.  rec(g, s) reads statistic s of rank g.
+template <typename Rec>
+__device__ __forceinline__ void sh_merge(const Rec& rec, int G, bool want_var, float& M, float& S, float& mean,
+                                         float& var, float& am) {
+    M = -INFINITY; am = 0.f;
+    for (int g = 0; g < G; ++g) {
+        const float mg = rec(g, 0);
+        if (mg > M) { M = mg; am = rec(g, 4); }
+    }
+    S = 0.f;
+    float s1 = 0.f;
+    for (int g = 0; g < G; ++g) {
+        const float w = rec(g, 1) * __expf(rec(g, 0) - M);
+        S += w;
+        s1 = fmaf(w, rec(g, 2), s1);
+    }
+    mean = __fdiv_rn(s1, S);
+    var = 0.f;
+    if (want_var) {
+        float m2 = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const float sc = __expf(rec(g, 0) - M);
+            const float c = rec(g, 2) - mean;
+            m2 += rec(g, 3) * sc + rec(g, 1) * sc * c * c;
+        }
+        var = __fdiv_rn(m2, S);
+    }
+}
+
+// Reduce-scatter form, step 2: this rank merges the G records of ITS slice of the pixels.  recv [G][5][slice]
+// (block g = rank g's statistics of my pixels, what the all-to-all delivered) -> merged [5][slice]:
+// M, log S, mean, variance, arg-max.
+__global__ void __launch_bounds__(SH_NT) shard_merge_slice_kernel(const float* __restrict__ recv,
+                                                                  float* __restrict__ merged, int G, int slice) {
+    const int i = blockIdx.x * SH_NT + threadIdx.x;
+    if (i >= slice) return;
+    auto rec = [&](int g, int s) { return recv[((long long)g * SH_NSTAT + s) * slice + i]; };
+    float M, S, mean, var, am;
+    sh_merge(rec, G, true, M, S, mean, var, am);
+    merged[i] = M; merged[slice + i] = logf(S); merged[2 * slice + i] = mean; merged[3 * slice + i] = var;
+    merged[4 * slice + i] = am;
+}
+
+// Reduce-scatter form, step 3: all [G][5][slice] holds the merged record of every pixel (block g = the slice rank g
+// merged, what the all-gather delivered): replicated per-pixel products and the local planes of the log-softmax.
+__global__ void __launch_bounds__(SH_NT) shard_finish_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ all,
+                                                             float* __restrict__ logp, float* __restrict__ depth,
+                                                             float* __restrict__ var, long long* __restrict__ argmax,
+                                                             int B, int D, int HW, int slice) {
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * SH_NT + threadIdx.x;
+    if (q >= HW) return;
+    const long long n = (long long)B * HW, pix = (long long)b * HW + q;
+    const float M = all[sh_stat_index(pix, 0, n, slice)], ls = all[sh_stat_index(pix, 1, n, slice)];
+    if (depth != nullptr) depth[pix] = all[sh_stat_index(pix, 2, n, slice)];
+    if (var != nullptr) var[pix] = all[sh_stat_index(pix, 3, n, slice)];
+    if (argmax != nullptr) argmax[pix] = (long long)all[sh_stat_index(pix, 4, n, slice)];
+    if (logp != nullptr) {
+        const float* p = x + (long long)b * D * HW + q;
+        float* o = logp + (long long)b * D * HW + q;
+        int k = 0;
+        for (; k + 8 <= D; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = ld_stream(p + (long long)(k + j) * HW);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_stream(o + (long long)(k + j) * HW, (v[j] - M) - ls);
+        }
+        for (; k < D; ++k) st_stream(o + (long long)k * HW, (ld_stream(p + (long long)k * HW) - M) - ls);
+    }
 }
 
 // gathered [G][5][B*HW] (rank order = plane order).  One thread per pixel merges the G records, writes the
@@ -144,27 +233,10 @@ __global__ void __launch_bounds__(SH_NT) shard_merge_finish_kernel(const float* 
     if (q >= HW) return;
     const long long n = (long long)B * HW, pix = (long long)b * HW + q;
     const long long gs = (long long)SH_NSTAT * n;
-    float M = -INFINITY, am = 0.f;
-    for (int g = 0; g < G; ++g) {
-        const float mg = gathered[g * gs + pix];
-        if (mg > M) { M = mg; am = gathered[g * gs + 4 * n + pix]; }    // strict: the first rank attaining M wins
-    }
-    float S = 0.f, s1 = 0.f;
-    for (int g = 0; g < G; ++g) {
-        const float w = gathered[g * gs + n + pix] * __expf(gathered[g * gs + pix] - M);
-        S += w;
-        s1 = fmaf(w, gathered[g * gs + 2 * n + pix], s1);
-    }
-    const float mean = __fdiv_rn(s1, S);
-    if (var != nullptr) {
-        float m2 = 0.f;
-        for (int g = 0; g < G; ++g) {
-            const float sc = __expf(gathered[g * gs + pix] - M);
-            const float c = gathered[g * gs + 2 * n + pix] - mean;
-            m2 += gathered[g * gs + 3 * n + pix] * sc + gathered[g * gs + n + pix] * sc * c * c;
-        }
-        var[pix] = __fdiv_rn(m2, S);
-    }
+    auto rec = [&](int g, int s) { return gathered[g * gs + (long long)s * n + pix]; };
+    float M, S, mean, vr, am;
+    sh_merge(rec, G, var != nullptr, M, S, mean, vr, am);
+    if (var != nullptr) var[pix] = vr;
     if (depth != nullptr) depth[pix] = mean;
     if (argmax != nullptr) argmax[pix] = (long long)am;
     if (logp != nullptr) {
@@ -184,29 +256,30 @@ __global__ void __launch_bounds__(SH_NT) shard_merge_finish_kernel(const float* 
 }
 
 template <int DL, int T>
-static void launch_stats(const float* x, const float* d, float* stats, int B, int HW, int off, cudaStream_t st) {
+static void launch_stats(const float* x, const float* d, float* stats, int B, int HW, int off, int slice,
+                         cudaStream_t st) {
     constexpr int PIX = SH_NT / T;
     dim3 grid((HW + PIX - 1) / PIX, B);
-    shard_stats_kernel<DL, T><<<grid, SH_NT, 0, st>>>(x, d, stats, B, HW, off);
+    shard_stats_kernel<DL, T><<<grid, SH_NT, 0, st>>>(x, d, stats, B, HW, off, slice);
 }
 
 }  // namespace dpv
 
 extern "C" int dpv_shard_stats(const float* x, const float* d_local, float* stats, int B, int D, int HW,
-                               int plane_offset, void* stream) {
+                               int plane_offset, int slice, void* stream) {
     using namespace dpv;
-    DPV_CHECK_ARG(x && d_local && stats && B > 0 && D > 0 && HW > 0 && plane_offset >= 0);
+    DPV_CHECK_ARG(x && d_local && stats && B > 0 && D > 0 && HW > 0 && plane_offset >= 0 && slice >= 0);
     if (B > 65535) return DPV_E_UNSUPP;
     cudaStream_t st = (cudaStream_t)stream;
     switch (D) {
-        case 8: launch_stats<8, 1>(x, d_local, stats, B, HW, plane_offset, st); break;
-        case 16: launch_stats<16, 1>(x, d_local, stats, B, HW, plane_offset, st); break;
-        case 32: launch_stats<32, 1>(x, d_local, stats, B, HW, plane_offset, st); break;
-        case 64: launch_stats<64, 2>(x, d_local, stats, B, HW, plane_offset, st); break;
-        case 128: launch_stats<128, 4>(x, d_local, stats, B, HW, plane_offset, st); break;
+        case 8: launch_stats<8, 1>(x, d_local, stats, B, HW, plane_offset, slice, st); break;
+        case 16: launch_stats<16, 1>(x, d_local, stats, B, HW, plane_offset, slice, st); break;
+        case 32: launch_stats<32, 1>(x, d_local, stats, B, HW, plane_offset, slice, st); break;
+        case 64: launch_stats<64, 2>(x, d_local, stats, B, HW, plane_offset, slice, st); break;
+        case 128: launch_stats<128, 4>(x, d_local, stats, B, HW, plane_offset, slice, st); break;
         default: {
             dim3 grid((HW + SH_NT - 1) / SH_NT, B);
-            shard_stats_generic_kernel<<<grid, SH_NT, 0, st>>>(x, d_local, stats, B, D, HW, plane_offset);
+            shard_stats_generic_kernel<<<grid, SH_NT, 0, st>>>(x, d_local, stats, B, D, HW, plane_offset, slice);
         }
     }
     DPV_LAUNCH_END();
@@ -222,6 +295,26 @@ extern "C" int dpv_shard_merge_finish(const float* x, const float* gathered, flo
     dim3 grid((HW + SH_NT - 1) / SH_NT, B);
     shard_merge_finish_kernel<<<grid, SH_NT, 0, (cudaStream_t)stream>>>(x, gathered, logp, depth, variance,
                                                                          (long long*)argmax, G, B, D, HW);
+    DPV_LAUNCH_END();
+    return 0;
+}
+
+extern "C" int dpv_shard_merge_slice(const float* recv, float* merged, int G, int slice, void* stream) {
+    using namespace dpv;
+    DPV_CHECK_ARG(recv && merged && G > 0 && slice > 0);
+    shard_merge_slice_kernel<<<(slice + SH_NT - 1) / SH_NT, SH_NT, 0, (cudaStream_t)stream>>>(recv, merged, G, slice);
+    DPV_LAUNCH_END();
+    return 0;
+}
+
+extern "C" int dpv_shard_finish(const float* x, const float* all, float* logp, float* depth, float* variance,
+                                int64_t* argmax, int B, int D, int HW, int slice, void* stream) {
+    using namespace dpv;
+    DPV_CHECK_ARG(x && all && B > 0 && D > 0 && HW > 0 && slice > 0);
+    if (B > 65535) return DPV_E_UNSUPP;
+    dim3 grid((HW + SH_NT - 1) / SH_NT, B);
+    shard_finish_kernel<<<grid, SH_NT, 0, (cudaStream_t)stream>>>(x, all, logp, depth, variance, (long long*)argmax, B,
+                                                                  D, HW, slice);
     DPV_LAUNCH_END();
     return 0;
 }

@@ -26,7 +26,7 @@ if ROOT not in sys.path:
 class TorchShardStandIn:
     """What csrc/shard.cu computes, in torch CPU ops (test stand-in for CudaShardKernels)."""
 
-    def local_stats(self, x, d_local, lo, out=None):
+    def local_stats(self, x, d_local, lo, out=None, slice_len=0):
         B, Dl, HW = x.shape
         m = x.max(dim=1).values
         first = (x == m.unsqueeze(1)).float().argmax(dim=1)          # first maximum wins inside the shard
@@ -35,10 +35,40 @@ class TorchShardStandIn:
         mu = (e * d_local.view(1, -1, 1)).sum(1) / s0
         m2 = (e * (d_local.view(1, -1, 1) - mu.unsqueeze(1)) ** 2).sum(1)
         st = torch.stack([m, s0, mu, m2, (first + lo).float()]).reshape(5, B * HW).contiguous()
+        if slice_len:                                                # slice-major [G, 5, slice] (all-to-all layout)
+            G = out.shape[0]
+            pad = torch.zeros((5, G * slice_len))
+            pad[:, :B * HW] = st
+            st = pad.reshape(5, G, slice_len).permute(1, 0, 2).contiguous()
         if out is not None:
             out.copy_(st)
             return out
         return st
+
+    @staticmethod
+    def _merge(g):
+        """g [G, 5, n] -> M, S, mean, var, arg-max (first rank attaining the maximum)."""
+        m, s0, mu, m2, am = g[:, 0], g[:, 1], g[:, 2], g[:, 3], g[:, 4]
+        M = m.max(dim=0).values
+        sc = torch.exp(m - M.unsqueeze(0))
+        w = s0 * sc
+        S = w.sum(0)
+        mean = (w * mu).sum(0) / S
+        var = (m2 * sc + w * (mu - mean.unsqueeze(0)) ** 2).sum(0) / S
+        first_rank = (m == M.unsqueeze(0)).float().argmax(dim=0)
+        return M, S, mean, var, torch.gather(am, 0, first_rank.unsqueeze(0))[0]
+
+    def merge_slice(self, recv, out):
+        M, S, mean, var, am = self._merge(torch.nan_to_num(recv))
+        out.copy_(torch.stack([M, torch.log(S), mean, var, am]))
+        return out
+
+    def finish(self, x, merged_all, want_logp, want_var, want_argmax):
+        B, Dl, HW = x.shape
+        G, _, sl = merged_all.shape
+        flat = merged_all.permute(1, 0, 2).reshape(5, G * sl)[:, :B * HW].reshape(5, B, HW)
+        logp = (x - flat[0].unsqueeze(1)) - flat[1].unsqueeze(1) if want_logp else None
+        return logp, flat[2], (flat[3] if want_var else None), (flat[4].long() if want_argmax else None)
 
     def merge_finish(self, x, gathered, want_logp, want_var, want_argmax):
         B, Dl, HW = x.shape
@@ -90,22 +120,23 @@ def _worker(rank, world, port, out_dir):
         x[0, 3, 0, :] = x[0, 8, 0, :] = 50.0                       # tie across the two shards: first wins
         d = synth.depth_candidates(5.0, 40.0, D, 1.0)
         lo, hi = sharding.plane_range(D, rank, world)
-        head = sharding.PlaneShardedHead(D, local=TorchShardStandIn())
-        assert (head.lo, head.hi) == (lo, hi)
-        out = head(x[:, lo:hi].contiguous(), d)
         ref = torch.log_softmax(x, 1)
         dd = torch.from_numpy(d.astype(np.float32)).view(1, D, 1, 1)
         p = ref.exp()
         mean = (p * dd).sum(1)
         var = (p * (dd - mean.unsqueeze(1)) ** 2).sum(1)
-        assert float((out["logp"] - ref[:, lo:hi]).abs().max()) < 1e-5
-        assert float((out["depth"] - mean).abs().max()) < 1e-4
-        assert float(((out["variance"] - var).abs() / var.clamp_min(1e-3)).max()) < 1e-4
-        assert torch.equal(out["argmax"], torch.argmax(ref, 1))
-        # every rank ends up with the same replicated per-pixel products
-        rep = [None] * world
-        dist.all_gather_object(rep, (out["depth"].numpy().tobytes(), out["argmax"].numpy().tobytes()))
-        assert all(r == rep[0] for r in rep)
+        for exchange in ("gather", "scatter"):      # one all-gather / all-to-all + all-gather (B*H*W = 70 pixels:
+            head = sharding.PlaneShardedHead(D, local=TorchShardStandIn(), exchange=exchange)   # ragged slices)
+            assert (head.lo, head.hi) == (lo, hi)
+            out = head(x[:, lo:hi].contiguous(), d)
+            assert float((out["logp"] - ref[:, lo:hi]).abs().max()) < 1e-5, exchange
+            assert float((out["depth"] - mean).abs().max()) < 1e-4, exchange
+            assert float(((out["variance"] - var).abs() / var.clamp_min(1e-3)).max()) < 1e-4, exchange
+            assert torch.equal(out["argmax"], torch.argmax(ref, 1)), exchange
+            # every rank ends up with the same replicated per-pixel products
+            rep = [None] * world
+            dist.all_gather_object(rep, (out["depth"].numpy().tobytes(), out["argmax"].numpy().tobytes()))
+            assert all(r == rep[0] for r in rep)
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
