@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=index,name,clocks.max.sm --format=csv > $O/gpus_n$N.csv
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29510 tools/nccl_plane_shard.py > $O/nccl_plane_shard_n$N.txt 2> $O/nccl_plane_shard_n$N.err; echo "plane shard N=$N rc=$?"; cat $O/nccl_plane_shard_n$N.txt
 for w in $WLS; do
-  steps=200; [ $w != stereo ] && steps=50
+  steps=200
   timeout 900 $TR --master-port 29511 bench.py --gpus $N --workload $w --steps $steps --warmup 10 > $O/bench_${w}_n$N.json 2> $O/bench_${w}_n$N.err; echo "bench $w N=$N rc=$?"
   tail -2 $O/bench_${w}_n$N.err | cut -c1-300
 done
