@@ -223,6 +223,27 @@ int dpv_shard_finish(const float* x, const float* all, float* logp, float* depth
 int dpv_shard_merge_finish(const float* x, const float* gathered, float* logp, float* depth,
                            float* variance, int64_t* argmax, int G, int B, int D, int HW, void* stream);
 
+/* ---- the D -> D 3x3 convolutions before the 1/4-res soft-max -----------------------
+ * conv0 / conv0_1 (Conv2d(D, D, 3, 1, 1, bias) + LeakyReLU) and conv0_2 (Conv2d) followed by
+ * F.log_softmax(dim=1) (models/models.py:456-460, applied at :555-560 and :632-637; LeakyReLU models/models.py:38-46),
+ * D = 64.  Implicit GEMM on the tcgen05 tensor cores with the accumulator in TMEM, fp32 parity through split
+ * precision (TF32 x 3: hi*hi + lo*hi + hi*lo).  Activations travel between the layers in a PACKED form
+ * [B][H+2][W+2][64] (channels innermost, zero border = the convolution's padding), twice: hi (the TF32 value
+ * nearest to it) and lo (the TF32 value nearest to value - hi); dpv_conv3x3_packed_floats gives the size of one of the two.
+ *   dpv_conv3x3_pack          NCHW [B,64,H,W] -> packed hi / lo
+ *   dpv_conv3x3_pack_weights  torch weight [64,64,3,3] -> packed hi / lo [9 taps][64 out][64 in] (once per model)
+ *   dpv_conv3x3_d64           one convolution: packed in -> bias + epilogue (0 = none, 1 = LeakyReLU(slope),
+ *                             2 = log_softmax over the 64 channels) -> packed hi / lo for the next layer (out_hi /
+ *                             out_lo, both or neither) and / or NCHW [B,64,H,W] (out_nchw).
+ * C != 64 returns DPV_E_UNSUPP.  All buffers 16-byte aligned.
+ */
+int64_t dpv_conv3x3_packed_floats(int B, int H, int W);
+int dpv_conv3x3_pack(const float* x, float* packed_hi, float* packed_lo, int B, int C, int H, int W, void* stream);
+int dpv_conv3x3_pack_weights(const float* weight, float* w_hi, float* w_lo, int C_out, int C_in, void* stream);
+int dpv_conv3x3_d64(const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo,
+                    const float* bias, float* out_hi, float* out_lo, float* out_nchw, int B, int H, int W,
+                    int epilogue, float slope, void* stream);
+
 /* ---- eval metrics on the device ------------------------------------
  * dpv_depth_errors replaces img_utils.depth_error (utils/img_utils.py:17-22) around depthError
  * (external/deval_lib/src/evaluate_depth.h:19-119), batched: first/second [B,H,W] in the python

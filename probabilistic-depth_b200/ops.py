@@ -441,6 +441,60 @@ def head_ufield(x, d_candi, intr_up, mode="logits", logp=True, depth=True, varia
     return out
 
 
+# ----------------------------------------------------------------------------- 8f rank 2: D -> D convolutions
+class CostRefine:
+    """conv0 -> LeakyReLU -> conv0_1 -> LeakyReLU -> conv0_2 -> log_softmax over the depth bins, the block between
+    the cost volume and the 1/4-res BV (reference models/models.py:456-460,555-560), on the tcgen05 tensor cores
+    at fp32 parity (TF32 x 3).  Built once per model from the three (weight [64,64,3,3], bias [64]) pairs: the
+    weights are packed on the device here; `__call__(cost)` takes the cost volume [B,64,h,w] and returns the
+    log-DPV (and, with `want_logits`, conv0_2's output before the soft-max)."""
+
+    def __init__(self, weights, biases, slope=0.01):
+        lib = _lib.load()
+        if len(weights) != 3 or len(biases) != 3:
+            raise ValueError("three (weight, bias) pairs: conv0, conv0_1, conv0_2")
+        self.slope = float(slope)
+        self.w, self.b = [], []
+        for w, b in zip(weights, biases):
+            _need(w, "weight"), _need(b, "bias")
+            if tuple(w.shape) != (64, 64, 3, 3) or tuple(b.shape) != (64,):
+                raise ValueError("the tensor-core path is built for D = 64 channels and 3x3 filters")
+            hi = torch.empty((9, 64, 64), device=w.device, dtype=torch.float32)
+            lo = torch.empty_like(hi)
+            _lib.check(lib.dpv_conv3x3_pack_weights(_p(w.detach().contiguous()), _p(hi), _p(lo), 64, 64, _stream()))
+            self.w.append((hi, lo))
+            self.b.append(b.detach().contiguous().float())
+        self._buf = None
+
+    def __call__(self, cost, want_logits=False):
+        _need(cost, "cost")
+        cost = cost.contiguous()
+        B, C, H, W = cost.shape
+        if C != 64:
+            raise ValueError("cost volume must have 64 planes")
+        lib = _lib.load()
+        n = int(lib.dpv_conv3x3_packed_floats(B, H, W))
+        key = (B, H, W, str(cost.device))
+        if self._buf is None or self._buf[0] != key:
+            self._buf = (key, [torch.empty((n,), device=cost.device, dtype=torch.float32) for _ in range(4)])
+        a_hi, a_lo, b_hi, b_lo = self._buf[1]
+        st = _stream()
+        _lib.check(lib.dpv_conv3x3_pack(_p(cost), _p(a_hi), _p(a_lo), B, C, H, W, st))
+        _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[0][0]), _p(self.w[0][1]), _p(self.b[0]),
+                                       _p(b_hi), _p(b_lo), None, B, H, W, 1, self.slope, st))
+        _lib.check(lib.dpv_conv3x3_d64(_p(b_hi), _p(b_lo), _p(self.w[1][0]), _p(self.w[1][1]), _p(self.b[1]),
+                                       _p(a_hi), _p(a_lo), None, B, H, W, 1, self.slope, st))
+        out = torch.empty_like(cost)
+        logits = None
+        if want_logits:
+            logits = torch.empty_like(cost)
+            _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
+                                           None, None, _p(logits), B, H, W, 0, 0.0, st))
+        _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
+                                       None, None, _p(out), B, H, W, 2, 0.0, st))
+        return (out, logits) if want_logits else out
+
+
 # ----------------------------------------------------------------------------- K2b
 def correlation(x1, x2, max_displacement=4):
     """Local correlation [B,(2r+1)^2,H,W] (reference models/correlation_native.py:13-23)."""

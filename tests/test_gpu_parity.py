@@ -489,3 +489,38 @@ def test_host_pipeline_submit_wait_overlaps_batches_with_identical_results(dpv):
         for k in wnt:
             assert torch.equal(torch.nan_to_num(o[k].float(), nan=-7.0), torch.nan_to_num(wnt[k].float(), nan=-7.0)), k
     pipe.close()
+
+
+# ------------------------------------------------------------------------- 8f rank 2: D -> D 3x3 convolutions
+@pytest.mark.parametrize("B,h,w", [(2, 64, 96), (1, 16, 24), (3, 7, 13)])
+def test_cost_refine_convs_tensor_core_vs_torch_fp32(dpv, B, h, w):
+    """conv0 -> LeakyReLU -> conv0_1 -> LeakyReLU -> conv0_2 -> log_softmax (models/models.py:456-460,555-560) on the
+    tcgen05 tensor cores with TF32 x 3 split precision, against torch's fp32 convolutions on the CPU (no TF32, no
+    cuDNN): logits within 1e-4 relative of their scale, log-DPV within 1e-4, arg-max identical except inside that noise."""
+    g = torch.Generator().manual_seed(1234 + h)
+    std = (2.0 / (9 * 64)) ** 0.5                                  # models/models.py weight_init
+    ws = [torch.randn((64, 64, 3, 3), generator=g) * std for _ in range(3)]
+    bs = [torch.randn((64,), generator=g) * 0.1 for _ in range(3)]
+    cost = torch.randn((B, 64, h, w), generator=g) * 4.0 + 10.0    # a cost volume: positive, O(10)
+    F = torch.nn.functional
+    x = F.leaky_relu(F.conv2d(cost.double(), ws[0].double(), bs[0].double(), padding=1), 0.01)
+    x = F.leaky_relu(F.conv2d(x, ws[1].double(), bs[1].double(), padding=1), 0.01)
+    want_logits = F.conv2d(x, ws[2].double(), bs[2].double(), padding=1)
+    want = torch.log_softmax(want_logits, dim=1)
+    refine = dpv.ops.CostRefine([t.cuda() for t in ws], [t.cuda() for t in bs])
+    got, got_logits = refine(cost.cuda(), want_logits=True)
+    scale = float(want_logits.abs().max())
+    e_logits = float((got_logits.cpu().double() - want_logits).abs().max()) / scale
+    e_logp = float(((got.cpu().double() - want).abs() / want.abs().clamp_min(1.0)).max())
+    print("cost refine %dx%dx%d: logits scale %.1f, max error %.2e of it; log-DPV scaled error %.2e" % (B, h, w, scale, e_logits, e_logp))
+    assert e_logits <= 1e-4
+    assert e_logp <= 1e-4
+    flips = torch.argmax(got.cpu(), 1) != torch.argmax(want, 1)
+    top2 = torch.topk(want, 2, dim=1).values
+    assert not flips.any() or float((top2[:, 0] - top2[:, 1])[flips].max()) <= 2e-4
+    # fp32 reference on the same device (what the model runs: cuDNN, TF32 off) for the record
+    torch.backends.cudnn.allow_tf32 = False
+    y = F.leaky_relu(F.conv2d(cost.cuda(), ws[0].cuda(), bs[0].cuda(), padding=1), 0.01)
+    y = F.leaky_relu(F.conv2d(y, ws[1].cuda(), bs[1].cuda(), padding=1), 0.01)
+    y = F.conv2d(y, ws[2].cuda(), bs[2].cuda(), padding=1)
+    assert float((got_logits - y).abs().max()) <= 1e-4 * scale
