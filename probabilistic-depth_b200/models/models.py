@@ -239,6 +239,23 @@ class BaseModel(nn.Module):
     def init_weights(self):
         self.apply(_init_2d_only)
 
+    def _refine_logits(self, cost):
+        """conv0 -> conv0_1 -> conv0_2 (reference models/models.py:555-557,632-634).  D = 64 on a CUDA device without
+        autograd: the tcgen05 implicit-GEMM kernels at fp32 parity (ops.CostRefine; DPV_REFINE_TC=0 keeps cuDNN);
+        otherwise the nn.Conv2d modules themselves (same parameters)."""
+        import os
+        mods = (self.conv0[0], self.conv0_1[0], self.conv0_2)
+        if (cost.is_cuda and self.D == 64 and not torch.is_grad_enabled() and os.environ.get("DPV_REFINE_TC", "1") != "0"
+                and all(m.weight.shape == (64, 64, 3, 3) for m in mods)):
+            key = tuple((t.data_ptr(), t._version) for m in mods for t in (m.weight, m.bias))
+            hit = getattr(self, "_refine_tc", None)
+            if hit is None or hit[0] != key:       # (re)pack the weights when the parameters changed
+                hit = (key, ops.CostRefine([m.weight for m in mods], [m.bias for m in mods],
+                                           slope=self.conv0[1].negative_slope))
+                self._refine_tc = hit
+            return hit[1](cost, want_logits=True, want_logp=False)
+        return self.conv0_2(self.conv0_1(self.conv0(cost)))
+
     # -- encoder + cost volume + 1/4-res DPV (reference forward_encoder / forward_exp) -----------
     def _encode(self, mi, want_raw):
         rgb = mi["rgb"]
@@ -254,7 +271,7 @@ class BaseModel(nn.Module):
         cost = ops.sweep_cost_volume(feat_all[:, -1], feat_all[:, :-1], poses[:, :-1].contiguous(),
                                      mi["intrinsics"].float(), mi["unit_ray"].float(), mi["d_candi"],
                                      self.sigma_soft_max, dist="L2")
-        logits = self.conv0_2(self.conv0_1(self.conv0(cost)))
+        logits = self._refine_logits(cost)
         last = [feat_all[:, -1, :-3], half[:, -1]]
         first = [feat_all[:, 0, :-3], half[:, 0]]
         warped = None

@@ -456,6 +456,7 @@ class CostRefine:
         self.slope = float(slope)
         self.w, self.b = [], []
         for w, b in zip(weights, biases):
+            w, b = w.detach(), b.detach()      # parameters: packed copies, no graph (the kernels are forward-only)
             _need(w, "weight"), _need(b, "bias")
             if tuple(w.shape) != (64, 64, 3, 3) or tuple(b.shape) != (64,):
                 raise ValueError("the tensor-core path is built for D = 64 channels and 3x3 filters")
@@ -466,7 +467,7 @@ class CostRefine:
             self.b.append(b.detach().contiguous().float())
         self._buf = None
 
-    def __call__(self, cost, want_logits=False):
+    def __call__(self, cost, want_logits=False, want_logp=True):
         _need(cost, "cost")
         cost = cost.contiguous()
         B, C, H, W = cost.shape
@@ -484,15 +485,18 @@ class CostRefine:
                                        _p(b_hi), _p(b_lo), None, B, H, W, 1, self.slope, st))
         _lib.check(lib.dpv_conv3x3_d64(_p(b_hi), _p(b_lo), _p(self.w[1][0]), _p(self.w[1][1]), _p(self.b[1]),
                                        _p(a_hi), _p(a_lo), None, B, H, W, 1, self.slope, st))
-        out = torch.empty_like(cost)
-        logits = None
+        out = logits = None
         if want_logits:
             logits = torch.empty_like(cost)
             _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
                                            None, None, _p(logits), B, H, W, 0, 0.0, st))
-        _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
-                                       None, None, _p(out), B, H, W, 2, 0.0, st))
-        return (out, logits) if want_logits else out
+        if want_logp:
+            out = torch.empty_like(cost)
+            _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
+                                           None, None, _p(out), B, H, W, 2, 0.0, st))
+        if want_logits and want_logp:
+            return out, logits
+        return logits if want_logits else out
 
 
 # ----------------------------------------------------------------------------- K2b

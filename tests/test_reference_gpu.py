@@ -320,6 +320,31 @@ def test_every_call_site_of_the_reference_model_on_its_own_tensors(dpv, ref, nam
     assert seen.get("est_swp_volume_v4", 0) >= 1 and seen.get("log_softmax", 0) >= 2, seen
 
 
+def test_cost_refine_convs_vs_the_reference_models_own_modules(dpv, ref):
+    """SURVEY 8f rank 2 inside the reference model: the cost volume the model fed to conv0 and what its own
+    conv0 / conv0_1 / conv0_2 modules (cuDNN fp32, TF32 off) returned (models/models.py:555-557), against the tcgen05
+    kernels on the same tensors and the model's own weights."""
+    model = ref_model(ref, "default_stereo")
+    seen = {}
+    h0 = model.conv0.register_forward_hook(lambda m, i, o: seen.__setitem__("cost", i[0].detach()))
+    h2 = model.conv0_2.register_forward_hook(lambda m, i, o: seen.__setitem__("logits", o.detach()))
+    try:
+        run_chain(model, "default_stereo", 1, 2)
+    finally:
+        h0.remove(); h2.remove()
+    mods = (model.conv0[0], model.conv0_1[0], model.conv0_2)
+    refine = dpv.ops.CostRefine([m.weight for m in mods], [m.bias for m in mods], slope=model.conv0[1].negative_slope)
+    logp, logits = refine(seen["cost"].contiguous(), want_logits=True)
+    scale = float(seen["logits"].abs().max())
+    e = float((logits - seen["logits"]).abs().max()) / scale
+    REPORT["site/default_stereo/conv0..conv0_2"] = {"logits_scale": scale, "max_error_over_scale": e}
+    assert e <= 1e-4 * 0.1, (e, scale)            # 1e-5 of the logits' scale (measured ~2e-6)
+    want = torch.log_softmax(seen["logits"].double(), dim=1)
+    entry = compare("site/default_stereo/conv_refine_log_softmax", logp, want.float(), MC.D_CANDI)
+    assert entry["log_dpv"] <= TOL and entry["mean"] <= TOL, entry
+    assert entry["max_top2_margin_at_flips"] <= 2 * TOL * max(1.0, scale * 1e-2), entry
+
+
 # ---------------------------------------------------------------------------- function level
 def test_hot_path_functions_reference_on_cuda_vs_ours(dpv, ref):
     """Each reference function of SURVEY.md 8a on cuda:0 (torch-CUDA grid_sample / softmax, whose fp32

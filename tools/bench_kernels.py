@@ -163,6 +163,34 @@ def main():
         med, best = timeit(f, nrot)
         byt = B * (8 * h * w * D * 2 + 12 * h * w)
         res["warp_feature"] = dict(ms=med, best_ms=best, GBs=byt / med / 1e6, frac=byt / med / 1e6 / PEAK)
+    if want("refine"):
+        # conv0 -> LeakyReLU -> conv0_1 -> LeakyReLU -> conv0_2 -> log_softmax at [B,64,64,96]
+        F = torch.nn.functional
+        std = (2.0 / (9 * 64)) ** 0.5
+        ws = [torch.randn((64, 64, 3, 3), device="cuda") * std for _ in range(3)]
+        bs = [torch.randn((64,), device="cuda") * 0.1 for _ in range(3)]
+        costs = [torch.randn((B, D, h, w), device="cuda") * 4 + 10 for _ in range(nrot)]
+        refine = ops.CostRefine(ws, bs)
+        flops = 3 * 2.0 * B * h * w * 64 * 64 * 9
+
+        def torch_chain(i):
+            y = F.leaky_relu(F.conv2d(costs[i], ws[0], bs[0], padding=1), 0.01)
+            y = F.leaky_relu(F.conv2d(y, ws[1], bs[1], padding=1), 0.01)
+            return torch.log_softmax(F.conv2d(y, ws[2], bs[2], padding=1), dim=1)
+        med, best = timeit(lambda i: refine(costs[i]), nrot)
+        res["refine_tcgen05_tf32x3"] = dict(ms=med, best_ms=best, GBs=0.0, frac=0.0, TFLOPs=flops / med / 1e9)
+        for tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for _ in range(3):
+                torch_chain(0)
+            med, best = timeit(torch_chain, nrot)
+            res["refine_torch_cudnn_%s" % ("tf32" if tf32 else "fp32")] = dict(ms=med, best_ms=best, GBs=0.0, frac=0.0,
+                                                                              TFLOPs=flops / med / 1e9)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        for k in ("refine_tcgen05_tf32x3", "refine_torch_cudnn_fp32", "refine_torch_cudnn_tf32"):
+            print("%-26s %8.4f ms  %6.1f TFLOP/s (conv flops of the three layers)" % (k, res[k]["ms"], res[k]["TFLOPs"]))
     if want("corr"):
         x1 = [torch.randn((2, 32, 96, 208), device="cuda") for _ in range(nrot)]
         x2 = [torch.randn((2, 32, 96, 208), device="cuda") for _ in range(nrot)]

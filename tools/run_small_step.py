@@ -32,6 +32,12 @@ f = cu(s.randn(6, 1, 2, 11, 8, 16))
 p = cu(np.stack([np.stack([s.pose(None, (-7.0, 0, 0)), s.pose()])]).astype(np.float32))
 c2 = s.camera(16, 8, 1)
 dpv.ops.sweep_cost_volume(f[:, -1], f[:, :-1], p[:, :-1], cu(c2["intrinsics"]), cu(c2["unit_ray"]), d, 10.0, algo=4, log_softmax=False)
+# the tcgen05 convolution chain on a small cost volume
+ws = [cu(0.06 * s.randn(20 + i, 64, 64, 3, 3)) for i in range(3)]
+bs = [cu(0.1 * s.randn(30 + i, 64)) for i in range(3)]
+lp = dpv.ops.CostRefine(ws, bs)(cu(4 * s.randn(40, 2, 64, 16, 24) + 10))
+torch.cuda.synchronize()
+print("refine ok", float(torch.logsumexp(lp, 1).abs().max()))
 a = cu(np.abs(s.randn(8, 2, 32, 48)) + 1)
 dpv.ops.depth_errors(a, a * 1.1)
 torch.cuda.synchronize()
