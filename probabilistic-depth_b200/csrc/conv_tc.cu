@@ -13,14 +13,16 @@
 //     nine taps and any shift; rows before the first / after the last pixel are zero-filled by the copy engine.
 //     Outputs are computed for all padded positions (98 % are real pixels); border positions are written as zero,
 //     which IS the next convolution's padding.
-//   * D[p][o] = sum over 9 taps x 64 channels: 18 K-blocks of 32 channels, each 4 tcgen05.mma (M=128, N=64, K=8,
-//     kind::tf32) per product term; three terms  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is 2^-22
+//   * D[p][o] = sum over 9 taps x 64 channels.  A K-block is (filter row, 32 channels): ONE A tile of 136 pixels
+//     serves the row's three taps -- the dx = 0 / +1 taps read the same shared-memory tile one and two 128-byte rows
+//     further down (descriptor start address) -- so the activations are streamed 3 times per tile, not 9.  Each tap
+//     and K-block: 4 tcgen05.mma (M=128, N=64, K=8, kind::tf32) per product term; three terms  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is 2^-22
 //     relative).  216 MMAs per 128-pixel tile, issued by ONE thread.  The tensor core adds into its fp32
 //     accumulator with truncation, a bias that grows with the number of accumulation steps at full magnitude
 //     (one accumulator for all 216: 1.2e-5 of the logits' scale, measured): the hi*hi terms therefore go to three
 //     TMEM tiles (one per filter row, 24 steps each), the small cross terms to a fourth, and the epilogue adds
 //     the four in fp32 with rounding.
-//   * Warp roles: warp 0 = TMA producer (4 copies per K-block: A_hi, A_lo, W_hi, W_lo; 48 KB per stage, 4 stages),
+//   * Warp roles: warp 0 = TMA producer (per K-block A_hi, A_lo and W_hi / W_lo of three taps; 82 KB per stage, 2 stages),
 //     warp 1 = TMEM allocation + MMA issue (tcgen05.commit releases a stage / publishes the accumulator),
 //     warps 2-5 = epilogue: tcgen05.ld gives every thread ONE pixel with all 64 output channels in registers, so
 //     bias + LeakyReLU + re-split into the next layer's packed hi / lo, or bias + log-softmax over the 64 depth
@@ -36,11 +38,12 @@ namespace dpv {
 constexpr int CT_C = 64;                   // channels in = channels out = depth bins
 constexpr int CT_M = 128;                  // pixels per tile (UMMA M)
 constexpr int CT_KB = 32;                  // channels per K-block: 32 x 4 B = one 128-byte swizzle row
-constexpr int CT_NKB = 9 * (CT_C / CT_KB); // 18 K-blocks
-constexpr int CT_STAGES = 4;
-constexpr int CT_A_BYTES = CT_M * CT_KB * 4;    // 16 KB
-constexpr int CT_B_BYTES = CT_C * CT_KB * 4;    // 8 KB
-constexpr int CT_STAGE_BYTES = 2 * CT_A_BYTES + 2 * CT_B_BYTES;   // 48 KB
+constexpr int CT_NKB = 3 * (CT_C / CT_KB); // 6 K-blocks: (filter row, channel half); each serves the row's 3 taps
+constexpr int CT_STAGES = 2;
+constexpr int CT_AROWS = CT_M + 8;         // pixels per A tile: 128 + the two neighbours of the dx = -1 / +1 taps (+ pad)
+constexpr int CT_A_BYTES = CT_AROWS * CT_KB * 4;    // 17 KB (a multiple of the 1024-byte swizzle period)
+constexpr int CT_B_BYTES = CT_C * CT_KB * 4;        // 8 KB per tap
+constexpr int CT_STAGE_BYTES = 2 * CT_A_BYTES + 6 * CT_B_BYTES;   // A hi / lo + W hi / lo of three taps = 82 KB
 constexpr int CT_THREADS = 192;            // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
 constexpr int CT_NACC = 4;                 // accumulators: hi*hi per filter row (3) + the two cross terms (1)
 constexpr int CT_TMEM_COLS = CT_NACC * CT_C;   // 256 columns: four fp32 tiles of 128 lanes x 64 columns
@@ -64,6 +67,10 @@ __device__ __forceinline__ void ct_tma_2d(void* dst, const CUtensorMap* map, int
                  ::"r"(tm_smem(dst)), "l"(map), "r"(c0), "r"(c1), "r"(tm_smem(bar)) : "memory");
 }
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100).
+// The swizzle is a function of the shared-memory ADDRESS (bits 4-6 xor bits 7-9), for the copy engine that wrote
+// the tile and for the tensor core that reads it alike: a descriptor that starts one or two 128-byte rows into a
+// tile (the dx = 0 / +1 taps) reads those rows correctly with the base-offset field left at 0 (measured: setting
+// it to the row phase gives wrong results).
 __device__ __forceinline__ unsigned long long ct_smem_desc(const void* p) {
     const unsigned long long addr = (unsigned long long)(tm_smem(p) >> 4) & 0x3FFFull;
     return addr | (1ull << 16) | ((1024ull >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -121,15 +128,17 @@ conv3x3_d64_tc_kernel(const ConvArgs a, const __grid_constant__ ConvMaps maps) {
             for (int kb = 0; kb < CT_NKB; ++kb) {
                 const int s = kb % CT_STAGES, it = kb / CT_STAGES;
                 if (it > 0) tm_mbar_wait(&empty_bar[s], (it - 1) & 1);     // the MMAs of the previous use are done
-                const int tap = kb >> 1, half = kb & 1;
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                const int frow = kb >> 1, half = kb & 1;                    // filter row dy = frow - 1
                 unsigned char* st = stage0 + s * CT_STAGE_BYTES;
                 tm_mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
-                const int row = p0 + dy * Wp + dx;                          // may be < 0 or run past NP: zero-filled
+                const int row = p0 + (frow - 1) * Wp - 1;                   // dx = -1 tap's first pixel; < 0 / past NP: zero-filled
                 ct_tma_2d(st, &maps.a_hi, half * CT_KB, row, &full_bar[s]);
                 ct_tma_2d(st + CT_A_BYTES, &maps.a_lo, half * CT_KB, row, &full_bar[s]);
-                ct_tma_2d(st + 2 * CT_A_BYTES, &maps.w_hi, half * CT_KB, tap * CT_C, &full_bar[s]);
-                ct_tma_2d(st + 2 * CT_A_BYTES + CT_B_BYTES, &maps.w_lo, half * CT_KB, tap * CT_C, &full_bar[s]);
+                for (int j = 0; j < 3; ++j) {                               // the row's three taps
+                    unsigned char* wb = st + 2 * CT_A_BYTES + j * 2 * CT_B_BYTES;
+                    ct_tma_2d(wb, &maps.w_hi, half * CT_KB, (frow * 3 + j) * CT_C, &full_bar[s]);
+                    ct_tma_2d(wb + CT_B_BYTES, &maps.w_lo, half * CT_KB, (frow * 3 + j) * CT_C, &full_bar[s]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -142,17 +151,20 @@ conv3x3_d64_tc_kernel(const ConvArgs a, const __grid_constant__ ConvMaps maps) {
                 tm_mbar_wait(&full_bar[s], it & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned char* st = stage0 + s * CT_STAGE_BYTES;
-                const unsigned long long a_hi = ct_smem_desc(st), a_lo = ct_smem_desc(st + CT_A_BYTES);
-                const unsigned long long b_hi = ct_smem_desc(st + 2 * CT_A_BYTES),
-                                         b_lo = ct_smem_desc(st + 2 * CT_A_BYTES + CT_B_BYTES);
-                const int frow = kb / 6;                                   // filter row of this K-block's tap
+                const int frow = kb >> 1;                                  // filter row of this K-block
                 const unsigned d_main = tmem_d + (unsigned)(frow * CT_C), d_cross = tmem_d + (unsigned)(3 * CT_C);
 #pragma unroll
-                for (int k = 0; k < CT_KB / 8; ++k) {
-                    const unsigned long long adv = (unsigned long long)((k * 8 * 4) >> 4);   // 32 bytes along K
-                    ct_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % 6) | k) != 0);
-                    ct_mma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-                    ct_mma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+                for (int j = 0; j < 3; ++j) {                              // dx = j - 1: the A tile, j rows further down
+                    const unsigned long long a_hi = ct_smem_desc(st + j * 128), a_lo = ct_smem_desc(st + CT_A_BYTES + j * 128);
+                    const unsigned char* wb = st + 2 * CT_A_BYTES + j * 2 * CT_B_BYTES;
+                    const unsigned long long b_hi = ct_smem_desc(wb), b_lo = ct_smem_desc(wb + CT_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CT_KB / 8; ++k) {
+                        const unsigned long long adv = (unsigned long long)((k * 8 * 4) >> 4);   // 32 bytes along K
+                        ct_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb & 1) | j | k) != 0);
+                        ct_mma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | j | k) != 0);
+                        ct_mma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
+                    }
                 }
                 ct_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
             }
@@ -327,7 +339,7 @@ extern "C" int dpv_conv3x3_d64(const float* in_hi, const float* in_lo, const flo
     tm_encode_fn enc = tm_encoder();
     if (enc == nullptr) return DPV_E_UNSUPP;
     ConvMaps maps;
-    if (!ct_encode_2d(enc, &maps.a_hi, in_hi, (cuuint64_t)np, CT_M) || !ct_encode_2d(enc, &maps.a_lo, in_lo, (cuuint64_t)np, CT_M) ||
+    if (!ct_encode_2d(enc, &maps.a_hi, in_hi, (cuuint64_t)np, CT_AROWS) || !ct_encode_2d(enc, &maps.a_lo, in_lo, (cuuint64_t)np, CT_AROWS) ||
         !ct_encode_2d(enc, &maps.w_hi, w_hi, 9 * CT_C, CT_C) || !ct_encode_2d(enc, &maps.w_lo, w_lo, 9 * CT_C, CT_C))
         return DPV_E_UNSUPP;
     ConvArgs a;
