@@ -7,6 +7,8 @@
 Workloads (BASELINE.json configs; D=64 bins, image 256x384, features / cost volume 64x96, C=67, V=1, fp32):
   stereo   (default, configs[1]) default_stereo, batch 8 per GPU: cost volume (+ 1/4-res log-softmax) ->
            full-res head (log-softmax, E[d], Var, arg-max, 1/4 hand-off) fused with the uncertainty field.
+  stereo_refine  the same with the model's 1/4-res head between the cost volume and the soft-max: the three D -> D
+           3x3 convolutions on the tcgen05 tensor cores, random-init weights.
   feedback (configs[2]) default_mono_feedback: + feedback warp of the previous DPV and log_softmax(BV + resi);
            8 sequences per GPU, a step = one frame of every sequence (16 steps = the 16-frame sequence).
   upsample (configs[3]) default_mono_upsample: + LiDAR prior and Bayesian fusion; GLOBAL batch 32 split over
@@ -49,6 +51,9 @@ BASE = dict(V=1, C=67, D=64, h=64, w=96, H=256, W=384)
 WORKLOADS = {
     "stereo": dict(BASE, B=8, mode="default", pose="stereo", scaling="weak",
                    desc="default_stereo: batch 8/GPU, D=64, image 256x384, features 64x96, C=67, V=1"),
+    "stereo_refine": dict(BASE, B=8, mode="default", pose="stereo", scaling="weak", refine=True,
+                          desc="default_stereo with the model's 1/4-res head: cost volume -> conv0 / conv0_1 / conv0_2 "
+                               "(tcgen05, TF32x3) -> log-softmax -> full-res head + UF; batch 8/GPU, D=64, 256x384"),
     "feedback": dict(BASE, B=8, mode="feedback", pose="mono", scaling="weak",
                      desc="default_mono_feedback: 8 sequences/GPU, one frame of each per step (16 steps = the 16-frame "
                           "sequence), feedback warp + fusion, D=64, image 256x384, features 64x96, C=67, V=1"),
@@ -397,9 +402,15 @@ def run_ours(args, dpv, wl):
 
     # ---- the step and its input sets (rotated: more bytes than the 126 MB L2 between two uses) -------------
     if mode in ("default", "feedback", "upsample"):
+        refine = None
+        if wl.get("refine"):
+            gw = torch.Generator(device=dev).manual_seed(7)
+            std = (2.0 / (9 * 64)) ** 0.5                       # models/models.py weight_init
+            refine = dpv.ops.CostRefine([torch.randn((64, 64, 3, 3), device=dev, generator=gw) * std for _ in range(3)],
+                                        [torch.randn((64,), device=dev, generator=gw) * 0.1 for _ in range(3)])
         step = frame_mod.FrameStep(B, wl["V"], wl["C"], wl["D"], wl["h"], wl["w"], wl["H"], wl["W"], hi["d"],
                                    sigma=10.0, mode=mode, device=dev, fuse_uf=not args.no_fuse_uf,
-                                   fuse_lsm=not args.no_fuse_lsm)
+                                   fuse_lsm=not args.no_fuse_lsm, refine=refine)
         nset = 2 if B <= 16 else 1
         dsets = [to_dev(hi if i == 0 else host_inputs(dpv, wl, B, seed=rank + 1000 * i)) for i in range(nset)]
 

@@ -19,7 +19,9 @@ from . import _lib, ops
 
 class FrameStep:
     def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None,
-                 fuse_uf=True, fuse_lsm=True):
+                 fuse_uf=True, fuse_lsm=True, refine=None):
+        """refine: optional ops.CostRefine (conv0 -> conv0_1 -> conv0_2 -> log-softmax, models/models.py:555-560):
+        the 1/4-res BV is then the refined cost volume instead of the soft-max of the cost volume itself."""
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dev = dev
         self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W = B, V, C, D, h, w, H, W
@@ -43,7 +45,8 @@ class FrameStep:
         # TMA-fed kernel that has this epilogue needs 16-byte row strides.
         # The epilogue needs all planes of a pixel in one CTA, i.e. no plane split: only when the batch
         # alone fills the machine (the launcher splits planes below 148 x 8 warps of pixels).
-        self.fuse_lsm = bool(fuse_lsm) and (w % 4 == 0) and B * h * ((w + 31) // 32) >= 148 * 8
+        self.refine = refine
+        self.fuse_lsm = bool(fuse_lsm) and refine is None and (w % 4 == 0) and B * h * ((w + 31) // 32) >= 148 * 8
         # K3 + K5 in one pass (fuse_uf, default: the tile kernel of dpv_head_uftile.cu takes gen_ufield's
         # column sums while the probabilities are in registers: 0.094 ms per batch of 8 x 256 x 384) or as
         # dpv_head followed by dpv_ufield's three launches (0.075 + 0.040 ms; also what shapes the fused
@@ -86,7 +89,11 @@ class FrameStep:
             B, V, C, D, h, w, (V + 1) * chw, (V + 1) * chw, chw, (V + 1) * 16, 9, 3 * h * w,
             self.sigma, 0, self.sweep_algo, p(self.sweep_ws), st))
         hk("sweep", 1)
-        if not self.fuse_lsm:
+        if self.refine is not None:
+            hk("cost_refine", 0)
+            self.refine(self.cost, out=self.bv)
+            hk("cost_refine", 1)
+        elif not self.fuse_lsm:
             hk("head_quarter", 0)
             _lib.check(lib.dpv_head(p(self.cost), None, p(self.d), p(self.bv), None, None, None, None,
                                     None, B, D, h, w, ops.IN_LOGITS, st))
@@ -200,7 +207,9 @@ class FrameStep:
         B, V, C, D = self.B, self.V, self.C, self.D
         hw, HW = self.h * self.w, self.H * self.W
         k = {"sweep": 4 * hw * (C * (1 + V) + D) + 12 * hw}
-        if self.fuse_lsm:
+        if self.refine is not None:
+            k["cost_refine"] = 8 * hw * D          # cost volume in, log-DPV out (the packed intermediates stay in L2)
+        elif self.fuse_lsm:
             k["sweep"] += 4 * hw * D
         else:
             k["head_quarter"] = 8 * hw * D

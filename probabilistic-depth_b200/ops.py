@@ -467,7 +467,8 @@ class CostRefine:
             self.b.append(b.detach().contiguous().float())
         self._buf = None
 
-    def __call__(self, cost, want_logits=False, want_logp=True):
+    def __call__(self, cost, want_logits=False, want_logp=True, out=None):
+        """`out`: optional pre-allocated [B,64,h,w] tensor for the log-DPV (no allocation on the path)."""
         _need(cost, "cost")
         cost = cost.contiguous()
         B, C, H, W = cost.shape
@@ -485,13 +486,15 @@ class CostRefine:
                                        _p(b_hi), _p(b_lo), None, B, H, W, 1, self.slope, st))
         _lib.check(lib.dpv_conv3x3_d64(_p(b_hi), _p(b_lo), _p(self.w[1][0]), _p(self.w[1][1]), _p(self.b[1]),
                                        _p(a_hi), _p(a_lo), None, B, H, W, 1, self.slope, st))
-        out = logits = None
+        logits = None
+        if not want_logp:
+            out = None
         if want_logits:
             logits = torch.empty_like(cost)
             _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
                                            None, None, _p(logits), B, H, W, 0, 0.0, st))
         if want_logp:
-            out = torch.empty_like(cost)
+            out = torch.empty_like(cost) if out is None else out
             _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
                                            None, None, _p(out), B, H, W, 2, 0.0, st))
         if want_logits and want_logp:

@@ -323,3 +323,35 @@ def test_fused_head_ufield_equals_two_kernel_path(dpv, D, H, W):
     ok = ~torch.isnan(uf2)
     assert int(ok.sum()) > 0
     assert float(((fused["uf"][ok] - uf2[ok]).abs() / uf2[ok].abs().clamp_min(1e-6)).max()) < 1e-5
+
+
+def test_frame_step_with_the_models_quarter_res_head(dpv):
+    """FrameStep(refine=CostRefine): the 1/4-res BV is log_softmax(conv0_2(conv0_1(conv0(cost)))) (models/models.py:555-560)
+    instead of the soft-max of the cost volume; everything else is unchanged; the step replays from a CUDA graph."""
+    frame = importlib.import_module("probabilistic-depth_b200.frame")
+    s = dpv.synth
+    B, V, C, D, h, w, H, W = 2, 1, 19, 64, 16, 24, 64, 96
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(w, h, B)
+    g = torch.Generator().manual_seed(3)
+    ws = [(torch.randn((64, 64, 3, 3), generator=g) * 0.06).cuda() for _ in range(3)]
+    bs = [(torch.randn((64,), generator=g) * 0.1).cuda() for _ in range(3)]
+    args = (cu(s.randn(1, B, V + 1, C, h, w)), cu(s.stereo_poses(B)), cu(cam["intrinsics"]), cu(cam["unit_ray"]),
+            cu(s.ground_plane_logits(2, B, H, W, d, cam["intrinsics_up"][0])), cu(cam["intrinsics_up"]))
+    plain = frame.FrameStep(B, V, C, D, h, w, H, W, d)
+    plain.run(*args)
+    step = frame.FrameStep(B, V, C, D, h, w, H, W, d, refine=dpv.ops.CostRefine(ws, bs))
+    step.run(*args)
+    torch.cuda.synchronize()
+    assert torch.equal(step.cost, plain.cost) and torch.equal(step.refined, plain.refined) and torch.equal(step.argmax, plain.argmax)
+    F = torch.nn.functional
+    x = F.leaky_relu(F.conv2d(step.cost.double(), ws[0].double(), bs[0].double(), padding=1), 0.01)
+    x = F.leaky_relu(F.conv2d(x, ws[1].double(), bs[1].double(), padding=1), 0.01)
+    want = torch.log_softmax(F.conv2d(x, ws[2].double(), bs[2].double(), padding=1), dim=1)
+    assert scaled_err(step.bv, want.float()) < 1e-4
+    first = step.bv.clone()
+    graph = step.capture(*args)
+    step.bv.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(step.bv, first)
