@@ -286,6 +286,20 @@ def local_correlation(x1, x2, max_displacement=4):
     return torch.cat(planes, 1)
 
 
+# --------------------------------------------------------------- 8f rank 2
+def cost_refine(cost, weights, biases, slope=0.01):
+    """conv0 -> LeakyReLU -> conv0_1 -> LeakyReLU -> conv0_2 -> log_softmax over the depth bins
+    (models/models.py:456-460 definitions with conv2d_leakyRelu :38-46, applied at :555-560 and :632-637):
+    Conv2d(D, D, 3, stride 1, padding 1, bias), nn.LeakyReLU() default slope 0.01.  Evaluated in float64 so that
+    the oracle carries no summation-order noise of its own.  Returns (log-DPV, conv0_2 output) as float64."""
+    x = cost.double()
+    for i in range(3):
+        x = F.conv2d(x, weights[i].double(), biases[i].double(), stride=1, padding=1)
+        if i < 2:
+            x = F.leaky_relu(x, slope)
+    return F.log_softmax(x, dim=1), x
+
+
 # ------------------------------------------------------------- whole-frame port
 def frame_hot_path(ref, src, d_candi, R, t, K, rays, sigma, logits_quarter, logits_full,
                    intr_up):

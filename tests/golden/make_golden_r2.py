@@ -8,6 +8,9 @@ sweep_wide.npz  : est_swp_volume_v4 (warping/homography.py:98-135) on images wid
                   cases.sweep_wide_case(...)["sub"] is stored.
 ufield_cfgx.npz : gen_ufield (utils/img_utils.py:268-358) called with cfgx, i.e. the quash_limit branch
                   (:325-332) the ROS caller uses (ros/ros_net.py:279).
+conv_refine.npz : the reference BaseModel's own conv0 / conv0_1 / conv0_2 modules + F.log_softmax
+                  (models/models.py:456-460,555-560) on a seeded cost volume [2,64,12,20], fp32 CPU, with the
+                  module weights stored next to the result.
 """
 import os
 import sys
@@ -18,6 +21,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import cases  # noqa: E402
 import make_golden  # noqa: E402
 
@@ -50,7 +54,26 @@ def main():
         out[name + "_depthzero"] = dz.numpy()
         print(name, "finite UF columns", int(np.isfinite(uf.numpy()).all(1).sum()), "of", uf.shape[-1])
     np.savez(os.path.join(HERE, "ufield_cfgx.npz"), **out)
-    for f in ("sweep_wide.npz", "ufield_cfgx.npz"):
+    # the model's own modules
+    sys.path.insert(0, os.path.join(HERE))
+    import model_cases as MC
+    from oracle import reference_loader
+    ref = reference_loader.load()
+    torch.manual_seed(0)
+    model = ref.models.BaseModel(MC.cfg("default_stereo"), 0)
+    cost = torch.from_numpy((4.0 * np.random.RandomState(77).standard_normal((2, 64, 12, 20)) + 10.0).astype(np.float32))
+    with torch.no_grad():
+        logits = model.conv0_2(model.conv0_1(model.conv0(cost)))
+        bv = torch.nn.functional.log_softmax(logits, dim=1)
+    mods = (model.conv0[0], model.conv0_1[0], model.conv0_2)
+    out = {"cost": cost.numpy(), "logits": logits.numpy(), "bv": bv.numpy(),
+           "slope": np.float32(model.conv0[1].negative_slope)}
+    for i, m in enumerate(mods):
+        out["w%d" % i] = m.weight.detach().numpy()
+        out["b%d" % i] = m.bias.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "conv_refine.npz"), **out)
+    print("conv_refine logits range", float(logits.min()), float(logits.max()))
+    for f in ("sweep_wide.npz", "ufield_cfgx.npz", "conv_refine.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 

@@ -13,6 +13,8 @@ depth and variance within 1e-4 relative in fp32"):
                             CUDA and torch versions on C>=128 inputs, i.e. |values| ~ 0.1,
                             models/correlation_native.py:64; summation order differs, 2 ulp)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -524,3 +526,16 @@ def test_cost_refine_convs_tensor_core_vs_torch_fp32(dpv, B, h, w):
     y = F.leaky_relu(F.conv2d(y, ws[1].cuda(), bs[1].cuda(), padding=1), 0.01)
     y = F.conv2d(y, ws[2].cuda(), bs[2].cuda(), padding=1)
     assert float((got_logits - y).abs().max()) <= 1e-4 * scale
+
+
+def test_cost_refine_vs_reference_golden(dpv):
+    """The tcgen05 convolution chain against the reference BaseModel's own modules (fixture conv_refine.npz)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "conv_refine.npz"))
+    refine = dpv.ops.CostRefine([cu(g["w%d" % i]) for i in range(3)], [cu(g["b%d" % i]) for i in range(3)],
+                                slope=float(g["slope"]))
+    bv, logits = refine(cu(g["cost"]), want_logits=True)
+    scale = float(np.abs(g["logits"]).max())
+    assert float(np.abs(logits.cpu().numpy() - g["logits"]).max()) <= 1e-5 * scale
+    logclose(bv, g["bv"])
+    want, _ = O.cost_refine(T(g["cost"]), [T(g["w%d" % i]) for i in range(3)], [T(g["b%d" % i]) for i in range(3)], float(g["slope"]))
+    logclose(bv, want.float().numpy())

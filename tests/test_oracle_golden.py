@@ -5,6 +5,8 @@ The reference has no tests or golden vectors of its own for this path
 which imports the unmodified reference.  The oracle calls the same ATen ops, so
 agreement is expected to be bit-exact or within a few ulp.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -151,3 +153,16 @@ def test_numpy_restatement_warp_feature_and_softmax(golden):
     s = cases.softmax_case("small")
     np.testing.assert_allclose(ONP.log_softmax(s["x"], 1), golden("softmax")["small_logdpv"],
                                rtol=1e-5, atol=2e-6)
+
+
+def test_cost_refine_oracle_vs_the_reference_models_modules():
+    """the oracle's conv0 -> conv0_1 -> conv0_2 -> log_softmax (float64) against the reference
+    BaseModel's own modules run in fp32 on the CPU (tests/golden/conv_refine.npz, make_golden_r2.py)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "conv_refine.npz"))
+    T = torch.from_numpy
+    bv, logits = O.cost_refine(T(g["cost"]), [T(g["w%d" % i]) for i in range(3)], [T(g["b%d" % i]) for i in range(3)],
+                               float(g["slope"]))
+    scale = float(np.abs(g["logits"]).max())
+    assert float((logits - T(g["logits"]).double()).abs().max()) <= 2e-6 * scale      # fp32 summation noise of the reference
+    # (1.1e-5 measured: the fp32 convolutions of the reference's CPU build against float64)
+    assert float(((bv - T(g["bv"]).double()).abs() / T(g["bv"]).double().abs().clamp_min(1.0)).max()) <= 3e-5
