@@ -15,15 +15,23 @@
 //     which IS the next convolution's padding.
 //   * D[p][o] = sum over 9 taps x 64 channels.  A K-block is (filter row, 32 channels): ONE A tile of 136 pixels
 //     serves the row's three taps -- the dx = 0 / +1 taps read the same shared-memory tile one and two 128-byte rows
-//     further down (descriptor start address) -- so the activations are streamed 3 times per tile, not 9.  Each tap
-//     and K-block: 4 tcgen05.mma (M=128, N=64, K=8, kind::tf32) per product term; three terms  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is 2^-22
-//     relative).  216 MMAs per 128-pixel tile, issued by ONE thread.  The tensor core adds into its fp32
+//     further down (descriptor start address) -- so the activations are streamed 3 times per tile, not 9.  Three
+//     product terms  hi*hi + hi*lo + lo*hi  (the dropped lo*lo term is 2^-22 relative) in TWO tcgen05.mma per tap and
+//     K step (kind::tf32, M = 128, K = 8): A_hi x [W_hi ; W_lo] with N = 128 (the two weight tiles sit next to each
+//     other in the stage, so one descriptor covers both and A_hi is read once) and A_lo x W_hi with N = 64 into the
+//     cross-term columns.  144 MMAs per 128-pixel tile, issued by ONE thread.  The tensor core adds into its fp32
 //     accumulator with truncation, a bias that grows with the number of accumulation steps at full magnitude
-//     (one accumulator for all 216: 1.2e-5 of the logits' scale, measured): the hi*hi terms therefore go to three
-//     TMEM tiles (one per filter row, 24 steps each), the small cross terms to a fourth, and the epilogue adds
-//     the four in fp32 with rounding.
+//     (one accumulator for all steps: 1.2e-5 of the logits' scale, measured): even and odd K-blocks therefore
+//     accumulate into two separate TMEM tiles (36 steps each), and the epilogue adds cross terms and the two
+//     hi*hi sums in fp32 with rounding, small before large.
+//   * Persistent CTAs (one per SM, tiles round-robin), accumulators double-buffered in TMEM (2 x 256 columns): the
+//     epilogue of a tile overlaps the copies and MMAs of the next.  Measured on the way (B=8, 64x96, three layers
+//     + pack, graph-timed): one tile per CTA 0.1245 ms -> persistent + double-buffered 0.0982 -> N = 128 MMAs
+//     0.0857.  Timing experiments on the one-tile kernel: without the copies after the first two K-blocks 0.1230
+//     (copies were hidden), without the MMAs 0.0794 (= copies + epilogues: 202 MB per layer from L2 into shared
+//     memory in ~23 us, about 0.7 of the chip's L2 throughput); at 0.0857 the kernel sits on that L2 -> SM floor.
 //   * Warp roles: warp 0 = TMA producer (per K-block A_hi, A_lo and W_hi / W_lo of three taps; 82 KB per stage, 2 stages),
-//     warp 1 = TMEM allocation + MMA issue (tcgen05.commit releases a stage / publishes the accumulator),
+//     warp 1 = TMEM allocation + MMA issue (tcgen05.commit releases a stage / publishes the accumulators),
 //     warps 2-5 = epilogue: tcgen05.ld gives every thread ONE pixel with all 64 output channels in registers, so
 //     bias + LeakyReLU + re-split into the next layer's packed hi / lo, or bias + log-softmax over the 64 depth
 //     bins, happens in registers with no cross-thread step; NCHW stores are coalesced across the warp's 32 pixels.
@@ -45,8 +53,8 @@ constexpr int CT_A_BYTES = CT_AROWS * CT_KB * 4;    // 17 KB (a multiple of the 
 constexpr int CT_B_BYTES = CT_C * CT_KB * 4;        // 8 KB per tap
 constexpr int CT_STAGE_BYTES = 2 * CT_A_BYTES + 6 * CT_B_BYTES;   // A hi / lo + W hi / lo of three taps = 82 KB
 constexpr int CT_THREADS = 192;            // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
-constexpr int CT_NACC = 4;                 // accumulators: hi*hi per filter row (3) + the two cross terms (1)
-constexpr int CT_TMEM_COLS = CT_NACC * CT_C;   // 256 columns: four fp32 tiles of 128 lanes x 64 columns
+constexpr int CT_NACC = 4;                 // 64-column accumulator tiles per buffer: (hi*hi | cross) of the even and of the odd K-blocks
+constexpr int CT_TMEM_COLS = CT_NACC * CT_C;   // 256 columns per buffer: four fp32 tiles of 128 lanes x 64 columns; two buffers
 
 struct ConvMaps {
     CUtensorMap a_hi, a_lo;   // [NP pixels][64 ch] packed activations, box {32, 128}, SWIZZLE_128B
@@ -93,28 +101,34 @@ __device__ __forceinline__ float ct_hi(float x) {
     return __uint_as_float(r);
 }
 
-// One 128-pixel tile per CTA.
+__device__ __forceinline__ void ct_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tm_smem(bar)) : "memory");
+}
+
+// Persistent: CTA i takes tiles i, i + gridDim.x, ...  The accumulators are double-buffered in TMEM (2 x 256
+// columns = all 512), so the epilogue of one tile (TMEM -> registers -> global) runs while the copy engine and the
+// tensor core are already on the next; the stage ring keeps running across tiles.
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv3x3_d64_tc_kernel(const ConvArgs a, const __grid_constant__ ConvMaps maps) {
     extern __shared__ __align__(1024) unsigned char ct_smem[];
-    __shared__ unsigned long long full_bar[CT_STAGES], empty_bar[CT_STAGES], acc_bar;
+    __shared__ unsigned long long full_bar[CT_STAGES], empty_bar[CT_STAGES], acc_full[2], acc_empty[2];
     __shared__ unsigned tmem_base_s;
     __shared__ float bias_s[CT_C];
     // dynamic shared memory may start at any 16-byte boundary: the swizzled tiles need 1024
     unsigned char* stage0 = (unsigned char*)(((uintptr_t)ct_smem + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p0 = blockIdx.x * CT_M;                // first padded-grid position of the tile
     const int Wp = a.W + 2, Hp = a.H + 2;
+    const int ntiles = (a.NP + CT_M - 1) / CT_M;
 
     if (threadIdx.x < CT_C) bias_s[threadIdx.x] = __ldg(a.bias + threadIdx.x);
     if (threadIdx.x == 0) {
         for (int s = 0; s < CT_STAGES; ++s) { tm_mbar_init(&full_bar[s], 1); tm_mbar_init(&empty_bar[s], 1); }
-        tm_mbar_init(&acc_bar, 1);
+        for (int i = 0; i < 2; ++i) { tm_mbar_init(&acc_full[i], 1); tm_mbar_init(&acc_empty[i], CT_M); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {      // TMEM: one warp allocates (and later frees) the accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(tm_smem(&tmem_base_s)), "r"((unsigned)CT_TMEM_COLS) : "memory");
+                     ::"r"(tm_smem(&tmem_base_s)), "r"((unsigned)(2 * CT_TMEM_COLS)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -125,127 +139,149 @@ conv3x3_d64_tc_kernel(const ConvArgs a, const __grid_constant__ ConvMaps maps) {
     if (warp == 0) {
         // ===== TMA producer (one elected lane) =====
         if (lane == 0) {
-            for (int kb = 0; kb < CT_NKB; ++kb) {
-                const int s = kb % CT_STAGES, it = kb / CT_STAGES;
-                if (it > 0) tm_mbar_wait(&empty_bar[s], (it - 1) & 1);     // the MMAs of the previous use are done
-                const int frow = kb >> 1, half = kb & 1;                    // filter row dy = frow - 1
-                unsigned char* st = stage0 + s * CT_STAGE_BYTES;
-                tm_mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
-                const int row = p0 + (frow - 1) * Wp - 1;                   // dx = -1 tap's first pixel; < 0 / past NP: zero-filled
-                ct_tma_2d(st, &maps.a_hi, half * CT_KB, row, &full_bar[s]);
-                ct_tma_2d(st + CT_A_BYTES, &maps.a_lo, half * CT_KB, row, &full_bar[s]);
-                for (int j = 0; j < 3; ++j) {                               // the row's three taps
-                    unsigned char* wb = st + 2 * CT_A_BYTES + j * 2 * CT_B_BYTES;
-                    ct_tma_2d(wb, &maps.w_hi, half * CT_KB, (frow * 3 + j) * CT_C, &full_bar[s]);
-                    ct_tma_2d(wb + CT_B_BYTES, &maps.w_lo, half * CT_KB, (frow * 3 + j) * CT_C, &full_bar[s]);
+            int g = 0;                                                      // K-blocks issued so far (ring position)
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int p0 = tile * CT_M;                                 // first padded-grid position of the tile
+                for (int kb = 0; kb < CT_NKB; ++kb, ++g) {
+                    const int s = g % CT_STAGES, use = g / CT_STAGES;
+                    if (use > 0) tm_mbar_wait(&empty_bar[s], (use - 1) & 1);    // the MMAs of the previous use are done
+                    const int frow = kb >> 1, half = kb & 1;                // filter row dy = frow - 1
+                    unsigned char* st = stage0 + s * CT_STAGE_BYTES;
+                    tm_mbar_expect_tx(&full_bar[s], CT_STAGE_BYTES);
+                    const int row = p0 + (frow - 1) * Wp - 1;               // dx = -1 tap's first pixel; < 0 / past NP: zero-filled
+                    ct_tma_2d(st, &maps.a_hi, half * CT_KB, row, &full_bar[s]);
+                    ct_tma_2d(st + CT_A_BYTES, &maps.a_lo, half * CT_KB, row, &full_bar[s]);
+                    for (int j = 0; j < 3; ++j) {                           // the row's three taps
+                        unsigned char* wb = st + 2 * CT_A_BYTES + j * 2 * CT_B_BYTES;
+                        ct_tma_2d(wb, &maps.w_hi, half * CT_KB, (frow * 3 + j) * CT_C, &full_bar[s]);
+                        ct_tma_2d(wb + CT_B_BYTES, &maps.w_lo, half * CT_KB, (frow * 3 + j) * CT_C, &full_bar[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
         if (lane == 0) {
-            // instruction descriptor: D fp32, A / B TF32, both K-major, N = 64, M = 128
-            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(CT_C >> 3) << 17) | ((unsigned)(CT_M >> 4) << 24);
-            for (int kb = 0; kb < CT_NKB; ++kb) {
-                const int s = kb % CT_STAGES, it = kb / CT_STAGES;
-                tm_mbar_wait(&full_bar[s], it & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                unsigned char* st = stage0 + s * CT_STAGE_BYTES;
-                const int frow = kb >> 1;                                  // filter row of this K-block
-                const unsigned d_main = tmem_d + (unsigned)(frow * CT_C), d_cross = tmem_d + (unsigned)(3 * CT_C);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {                              // dx = j - 1: the A tile, j rows further down
-                    const unsigned long long a_hi = ct_smem_desc(st + j * 128), a_lo = ct_smem_desc(st + CT_A_BYTES + j * 128);
-                    const unsigned char* wb = st + 2 * CT_A_BYTES + j * 2 * CT_B_BYTES;
-                    const unsigned long long b_hi = ct_smem_desc(wb), b_lo = ct_smem_desc(wb + CT_B_BYTES);
-#pragma unroll
-                    for (int k = 0; k < CT_KB / 8; ++k) {
-                        const unsigned long long adv = (unsigned long long)((k * 8 * 4) >> 4);   // 32 bytes along K
-                        ct_mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb & 1) | j | k) != 0);
-                        ct_mma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | j | k) != 0);
-                        ct_mma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1);
-                    }
+            // instruction descriptors: D fp32, A / B TF32, both K-major, M = 128, N = 64 / 128
+            const unsigned idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(CT_M >> 4) << 24);
+            const unsigned idesc64 = idesc0 | ((unsigned)(CT_C >> 3) << 17), idesc128 = idesc0 | ((unsigned)(2 * CT_C >> 3) << 17);
+            int g = 0, t = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+                const int buf = t & 1;
+                if (t >= 2) {                      // the epilogue has read this buffer's previous tile out of TMEM
+                    tm_mbar_wait(&acc_empty[buf], ((t >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                ct_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+                const unsigned tmem_t = tmem_d + (unsigned)(buf * CT_TMEM_COLS);
+                for (int kb = 0; kb < CT_NKB; ++kb, ++g) {
+                    const int s = g % CT_STAGES, use = g / CT_STAGES;
+                    tm_mbar_wait(&full_bar[s], use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    unsigned char* st = stage0 + s * CT_STAGE_BYTES;
+                    // even K-blocks accumulate into columns [0, 128), odd ones into [128, 256): in each, the hi*hi
+                    // sum in the first 64 columns and the cross terms in the last 64
+                    const unsigned d_acc = tmem_t + (unsigned)((kb & 1) * 2 * CT_C);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {                          // dx = j - 1: the A tile, j rows further down
+                        const unsigned long long a_hi = ct_smem_desc(st + j * 128), a_lo = ct_smem_desc(st + CT_A_BYTES + j * 128);
+                        const unsigned char* wb = st + 2 * CT_A_BYTES + j * 2 * CT_B_BYTES;
+                        const unsigned long long b_both = ct_smem_desc(wb);      // W hi (64 rows) followed by W lo (64 rows)
+#pragma unroll
+                        for (int k = 0; k < CT_KB / 8; ++k) {
+                            const unsigned long long adv = (unsigned long long)((k * 8 * 4) >> 4);   // 32 bytes along K
+                            ct_mma_tf32(d_acc, a_hi + adv, b_both + adv, idesc128, ((kb >> 1) | j | k) != 0);   // hi*hi | hi*lo
+                            ct_mma_tf32(d_acc + CT_C, a_lo + adv, b_both + adv, idesc64, 1);                    // lo*hi
+                        }
+                    }
+                    ct_commit(&empty_bar[s]);      // frees the stage when these MMAs have read it
+                }
+                ct_commit(&acc_full[buf]);         // this tile's accumulators are complete
             }
-            ct_commit(&acc_bar);                   // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5, one pixel per thread, 64 channels in registers =====
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;               // row of the tile
-        const int p = p0 + m;                      // padded-grid position
-        tm_mbar_wait(&acc_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float v[CT_C];
+        const int per = Hp * Wp;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+            const int buf = t & 1;
+            const int p = tile * CT_M + m;         // padded-grid position
+            tm_mbar_wait(&acc_full[buf], (t >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float v[CT_C];
 #pragma unroll
-        for (int c = 0; c < CT_C; ++c) v[c] = bias_s[c];
-        {
-            const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16);
-            // cross terms first, then the three filter rows: small before large
+            for (int c = 0; c < CT_C; ++c) v[c] = bias_s[c];
+            {
+                const unsigned taddr = tmem_d + (unsigned)(buf * CT_TMEM_COLS) + ((unsigned)(q * 32) << 16);
+                // cross terms first (columns 64.., 192..), then the two hi*hi sums: small before large
 #pragma unroll
-            for (int acc = CT_NACC - 1; acc >= 0; --acc) {
+                for (int ai = 0; ai < CT_NACC; ++ai) {
+                    const int acc = ai == 0 ? 1 : ai == 1 ? 3 : ai == 2 ? 0 : 2;
 #pragma unroll
-                for (int c0 = 0; c0 < CT_C; c0 += 16) {
-                    unsigned r[16];
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-                                   "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
-                                   "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                                 : "r"(taddr + (unsigned)(acc * CT_C + c0)));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    for (int c0 = 0; c0 < CT_C; c0 += 16) {
+                        unsigned r[16];
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                                       "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+                                       "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                                     : "r"(taddr + (unsigned)(acc * CT_C + c0)));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[c0 + j] += __uint_as_float(r[j]);
+                        for (int j = 0; j < 16; ++j) v[c0 + j] += __uint_as_float(r[j]);
+                    }
                 }
             }
-        }
-        // where is this position on the padded grid
-        const int per = Hp * Wp;
-        const bool in_range = p < a.NP;
-        const int b = in_range ? p / per : 0;
-        const int rem = p - b * per;
-        const int yp = rem / Wp, xp = rem - yp * Wp;
-        const bool real = in_range && yp >= 1 && yp <= a.H && xp >= 1 && xp <= a.W;
-        if (a.epilogue == 1) {
+            // the accumulators are in registers: hand the TMEM buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            ct_mbar_arrive(&acc_empty[buf]);
+            // where is this position on the padded grid
+            const bool in_range = p < a.NP;
+            const int b = in_range ? p / per : 0;
+            const int rem = p - b * per;
+            const int yp = rem / Wp, xp = rem - yp * Wp;
+            const bool real = in_range && yp >= 1 && yp <= a.H && xp >= 1 && xp <= a.W;
+            if (a.epilogue == 1) {
 #pragma unroll
-            for (int c = 0; c < CT_C; ++c) v[c] = v[c] > 0.f ? v[c] : v[c] * a.slope;
-        } else if (a.epilogue == 2) {
-            float mx = v[0];
+                for (int c = 0; c < CT_C; ++c) v[c] = v[c] > 0.f ? v[c] : v[c] * a.slope;
+            } else if (a.epilogue == 2) {
+                float mx = v[0];
 #pragma unroll
-            for (int c = 1; c < CT_C; ++c) mx = fmaxf(mx, v[c]);
-            float s = 0.f;
+                for (int c = 1; c < CT_C; ++c) mx = fmaxf(mx, v[c]);
+                float s = 0.f;
 #pragma unroll
-            for (int c = 0; c < CT_C; ++c) s += __expf(v[c] - mx);
-            const float ls = logf(s);
+                for (int c = 0; c < CT_C; ++c) s += __expf(v[c] - mx);
+                const float ls = logf(s);
 #pragma unroll
-            for (int c = 0; c < CT_C; ++c) v[c] = (v[c] - mx) - ls;
-        }
-        if (a.out_hi != nullptr && in_range) {     // the next layer's packed input; border positions = its zero padding
-            float4* oh = reinterpret_cast<float4*>(a.out_hi + (long long)p * CT_C);
-            float4* ol = reinterpret_cast<float4*>(a.out_lo + (long long)p * CT_C);
-#pragma unroll
-            for (int c = 0; c < CT_C; c += 4) {
-                float4 h, l;
-                h.x = real ? ct_hi(v[c]) : 0.f; h.y = real ? ct_hi(v[c + 1]) : 0.f;
-                h.z = real ? ct_hi(v[c + 2]) : 0.f; h.w = real ? ct_hi(v[c + 3]) : 0.f;
-                l.x = real ? ct_hi(v[c] - h.x) : 0.f; l.y = real ? ct_hi(v[c + 1] - h.y) : 0.f;
-                l.z = real ? ct_hi(v[c + 2] - h.z) : 0.f; l.w = real ? ct_hi(v[c + 3] - h.w) : 0.f;
-                oh[c >> 2] = h; ol[c >> 2] = l;
+                for (int c = 0; c < CT_C; ++c) v[c] = (v[c] - mx) - ls;
             }
-        }
-        if (a.out_nchw != nullptr && real) {
-            const long long HW = (long long)a.H * a.W;
-            float* o = a.out_nchw + (long long)b * CT_C * HW + (long long)(yp - 1) * a.W + (xp - 1);
+            if (a.out_hi != nullptr && in_range) {     // the next layer's packed input; border positions = its zero padding
+                float4* oh = reinterpret_cast<float4*>(a.out_hi + (long long)p * CT_C);
+                float4* ol = reinterpret_cast<float4*>(a.out_lo + (long long)p * CT_C);
 #pragma unroll
-            for (int c = 0; c < CT_C; ++c) o[c * HW] = v[c];
+                for (int c = 0; c < CT_C; c += 4) {
+                    float4 h, l;
+                    h.x = real ? ct_hi(v[c]) : 0.f; h.y = real ? ct_hi(v[c + 1]) : 0.f;
+                    h.z = real ? ct_hi(v[c + 2]) : 0.f; h.w = real ? ct_hi(v[c + 3]) : 0.f;
+                    l.x = real ? ct_hi(v[c] - h.x) : 0.f; l.y = real ? ct_hi(v[c + 1] - h.y) : 0.f;
+                    l.z = real ? ct_hi(v[c + 2] - h.z) : 0.f; l.w = real ? ct_hi(v[c + 3] - h.w) : 0.f;
+                    oh[c >> 2] = h; ol[c >> 2] = l;
+                }
+            }
+            if (a.out_nchw != nullptr && real) {
+                const long long HW = (long long)a.H * a.W;
+                float* o = a.out_nchw + (long long)b * CT_C * HW + (long long)(yp - 1) * a.W + (xp - 1);
+#pragma unroll
+                for (int c = 0; c < CT_C; ++c) o[c * HW] = v[c];
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)CT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)(2 * CT_TMEM_COLS)) : "memory");
     }
 }
 
@@ -349,7 +385,15 @@ extern "C" int dpv_conv3x3_d64(const float* in_hi, const float* in_lo, const flo
     cudaError_t e = cudaFuncSetAttribute(conv3x3_d64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const unsigned tiles = (unsigned)((np + CT_M - 1) / CT_M);
-    conv3x3_d64_tc_kernel<<<tiles, CT_THREADS, smem, (cudaStream_t)stream>>>(a, maps);
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            return DPV_E_UNSUPP;
+        n_sm = n;
+    }
+    const unsigned grid = tiles < (unsigned)n_sm ? tiles : (unsigned)n_sm;     // persistent: one CTA per SM
+    conv3x3_d64_tc_kernel<<<grid, CT_THREADS, smem, (cudaStream_t)stream>>>(a, maps);
     DPV_LAUNCH_END();
     return 0;
 }
