@@ -244,6 +244,37 @@ int dpv_conv3x3_d64(const float* in_hi, const float* in_lo, const float* w_hi, c
                     const float* bias, float* out_hi, float* out_lo, float* out_nchw, int B, int H, int W,
                     int epilogue, float slope, void* stream);
 
+/* ---- SURVEY.md 8f rank 2, second half: Base3D, the 3-D convolutions of the feedback mode ---------------
+ * models/models.py:376-438: Conv3d(., 32, 3, 1, 1, bias=False) + BatchNorm3d (models/models.py:31-36) [+ ReLU]
+ * stacks over the volume [B, C, D, h, w] (applied at models/models.py:693).  Same tcgen05 / TMEM / TF32 x 3
+ * machinery as dpv_conv3x3_d64, for 32 channels: activations packed as [B][D+2][H+2][W+2][32] hi / lo
+ * (dpv_conv3d_packed_floats floats each), channels innermost, zero border.
+ *   dpv_conv3d_pack          NCDHW [B,C<=32,D,H,W] -> packed hi / lo (channels >= C zero)
+ *   dpv_conv3d_pack_weights  torch weight [C_out<=32][C_in<=32][3][3][3], optionally times scale[C_out] (a BatchNorm in
+ *                            eval with running statistics folded into the filter) -> packed hi / lo [27][32][32]
+ *   dpv_conv3d_c32           one convolution.  shift [32] (nullable = 0; the folded BatchNorm's shift) is added, then the
+ *                            packed residual (res_hi / res_lo, nullable), then ReLU (relu != 0).  Outputs, any
+ *                            combination: packed hi / lo for the next layer; out_c0 [B,D,H,W] = channel 0 (the
+ *                            32 -> 1 classifier, models/models.py:403); out_raw [positions][32] fp32 together with
+ *                            stats (double[64], caller-zeroed: per channel sum and sum of squares over the real
+ *                            voxels, +=) for a BatchNorm that uses BATCH statistics.  c_in = real input channels
+ *                            (K steps beyond them are skipped).
+ *   dpv_conv3d_bn_apply      BatchNorm with batch statistics (F.batch_norm(training=True): the unregistered
+ *                            dres_modules of Base3D never leave training mode, models/models.py:394-399): raw, stats
+ *                            -> (x - mean) / sqrt(biased var + eps) * gamma + beta, + residual, ReLU -> packed hi / lo.
+ *                            Running statistics are not updated.
+ */
+int64_t dpv_conv3d_packed_floats(int B, int D, int H, int W);
+int dpv_conv3d_pack(const float* x, float* packed_hi, float* packed_lo, int B, int C, int D, int H, int W, void* stream);
+int dpv_conv3d_pack_weights(const float* weight, const float* scale, float* w_hi, float* w_lo, int C_out, int C_in,
+                            void* stream);
+int dpv_conv3d_c32(const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo, const float* shift,
+                   const float* res_hi, const float* res_lo, float* out_hi, float* out_lo, float* out_c0,
+                   float* out_raw, double* stats, int B, int D, int H, int W, int relu, int c_in, void* stream);
+int dpv_conv3d_bn_apply(const float* raw, const double* stats, const float* gamma, const float* beta, float eps,
+                        const float* res_hi, const float* res_lo, float* out_hi, float* out_lo, int B, int D, int H,
+                        int W, int relu, void* stream);
+
 /* ---- eval metrics on the device ------------------------------------
  * dpv_depth_errors replaces img_utils.depth_error (utils/img_utils.py:17-22) around depthError
  * (external/deval_lib/src/evaluate_depth.h:19-119), batched: first/second [B,H,W] in the python

@@ -300,6 +300,34 @@ def cost_refine(cost, weights, biases, slope=0.01):
     return F.log_softmax(x, dim=1), x
 
 
+def base3d(volume, layers):
+    """Base3D.forward(volume, prob=False) (models/models.py:376-438, called at :693): dres0 -> residual blocks ->
+    classify, every convolution Conv3d(k=3, stride 1, padding 1, bias=False) (models/models.py:31-36, :403), float64.
+    layers: list of dicts {weight, bn: None | dict(gamma, beta, mean, var, eps, batch_stats), relu, block: None | "in"
+    | "out"}: "in" = first layer of a residual block (its input is the skip), "out" = the layer the skip is added to
+    (:421-422: curr = dres(curr) + curr, no ReLU after the sum).  batch_stats: the BatchNorm normalises with the
+    biased statistics of the batch (training mode / track_running_stats=False), else with its running statistics."""
+    x = volume.double()
+    skip = None
+    for L in layers:
+        if L.get("block") == "in":
+            skip = x
+        x = F.conv3d(x, L["weight"].double(), None, stride=1, padding=1)
+        bn = L.get("bn")
+        if bn is not None:
+            g, b = bn["gamma"].double(), bn["beta"].double()
+            if bn["batch_stats"]:
+                x = F.batch_norm(x, None, None, g, b, True, 0.0, float(bn["eps"]))
+            else:
+                x = F.batch_norm(x, bn["mean"].double(), bn["var"].double(), g, b, False, 0.0, float(bn["eps"]))
+        if L.get("block") == "out":
+            x = x + skip
+            skip = None
+        if L.get("relu"):
+            x = F.relu(x)
+    return x.squeeze(1)
+
+
 # ------------------------------------------------------------- whole-frame port
 def frame_hot_path(ref, src, d_candi, R, t, K, rays, sigma, logits_quarter, logits_full,
                    intr_up):

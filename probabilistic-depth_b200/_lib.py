@@ -42,6 +42,11 @@ PROTOTYPES = {
     "dpv_conv3x3_pack": (_c_i, [_c_fp] * 3 + [_c_i] * 4 + [_c_fp]),
     "dpv_conv3x3_pack_weights": (_c_i, [_c_fp] * 3 + [_c_i] * 2 + [_c_fp]),
     "dpv_conv3x3_d64": (_c_i, [_c_fp] * 8 + [_c_i] * 4 + [_c_f, _c_fp]),
+    "dpv_conv3d_packed_floats": (_c_i64, [_c_i] * 4),
+    "dpv_conv3d_pack": (_c_i, [_c_fp] * 3 + [_c_i] * 5 + [_c_fp]),
+    "dpv_conv3d_pack_weights": (_c_i, [_c_fp] * 4 + [_c_i] * 2 + [_c_fp]),
+    "dpv_conv3d_c32": (_c_i, [_c_fp] * 12 + [_c_i] * 6 + [_c_fp]),
+    "dpv_conv3d_bn_apply": (_c_i, [_c_fp] * 4 + [_c_f] + [_c_fp] * 4 + [_c_i] * 5 + [_c_fp]),
     "dpv_depth_errors_workspace_doubles": (_c_i64, [_c_i] * 3),
     "dpv_depth_errors": (_c_i, [_c_fp] * 3 + [_c_f, _c_i] + [_c_fp] * 3 + [_c_i] * 3 + [_c_fp]),
     "dpv_unc_rmse": (_c_i, [_c_fp] * 4 + [_c_i] * 3 + [_c_fp]),

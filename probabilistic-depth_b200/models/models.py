@@ -196,7 +196,35 @@ class Base3D(nn.Module):
                                       nn.Conv3d(feature_dim, 1, kernel_size=3, padding=1, stride=1, bias=False))
         self.apply(_init_weights)
 
+    def _tc(self, volume):
+        """The tcgen05 path (ops.Base3DConvs): CUDA, no autograd, at most 32 channels; DPV_BASE3D_TC=0 keeps cuDNN.
+        Re-packed when a parameter, a running statistic or a BatchNorm's mode changed.  NOTE: BatchNorms that
+        normalise with batch statistics do not get their running statistics updated on this path (the reference's
+        residual blocks never read theirs)."""
+        import os
+        if not (volume.is_cuda and not torch.is_grad_enabled() and os.environ.get("DPV_BASE3D_TC", "1") != "0"):
+            return None
+        convs = [self.dres0[0][0], self.dres0[2][0]] + [b[j][0] for b in self.dres_modules for j in (0, 2)] + \
+                [self.classify[0][0], self.classify[2]]
+        if any(c.weight.shape[0] > 32 or c.weight.shape[1] > 32 for c in convs) or self.classify[2].weight.shape[0] != 1:
+            return None
+        for i, blk in enumerate(self.dres_modules):
+            if next(blk.parameters()).device != volume.device:
+                self.dres_modules[i] = blk.to(volume.device)
+        bns = [self.dres0[0][1], self.dres0[2][1]] + [b[j][1] for b in self.dres_modules for j in (0, 2)] + [self.classify[0][1]]
+        key = tuple((c.weight.data_ptr(), c.weight._version) for c in convs) + \
+            tuple((b.weight.data_ptr(), b.weight._version, b.bias._version, b.training, b.track_running_stats,
+                   None if b.running_mean is None else (b.running_mean._version, b.running_var._version)) for b in bns)
+        hit = getattr(self, "_tc_net", None)
+        if hit is None or hit[0] != key:
+            hit = (key, ops.Base3DConvs.from_module(self))
+            self._tc_net = hit
+        return hit[1](volume)
+
     def forward(self, volume):
+        out = self._tc(volume)
+        if out is not None:
+            return out
         x = self.dres0(volume.contiguous())
         for i, blk in enumerate(self.dres_modules):
             if next(blk.parameters()).device != x.device:

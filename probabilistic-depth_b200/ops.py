@@ -502,6 +502,121 @@ class CostRefine:
         return logits if want_logits else out
 
 
+class Base3DConvs:
+    """Base3D, the 3-D convolution stack of the feedback mode (reference models/models.py:376-438, applied at :693):
+    dres0 (two Conv3d + BatchNorm3d + ReLU), `dres_count` residual blocks (Conv3d + BN + ReLU, Conv3d + BN, + input),
+    classify (Conv3d + BN + ReLU, Conv3d(32 -> 1)) over [B, C<=32, D, h, w], feature_dim = 32, on the tcgen05 tensor
+    cores at fp32 parity (TF32 x 3).  A BatchNorm in eval with running statistics is folded into its convolution; one
+    that uses batch statistics (training mode -- the reference's unregistered dres_modules never leave it -- or
+    track_running_stats = False) is computed from sums the convolution's epilogue accumulates (running statistics
+    are NOT updated by this path).  Built once per model with `from_module`; `__call__(volume)` returns the
+    residual [B, D, h, w] (`prob=False` in the reference)."""
+
+    def __init__(self, layers):
+        """layers: list of dicts {weight [Co,Ci,3,3,3], bn: None | dict(gamma, beta, mean, var, eps, batch_stats),
+        relu: bool, block: None | "in" | "out"} -- "in" marks the first layer of a residual block (its input is the
+        skip), "out" the layer whose result the skip is added to."""
+        lib = _lib.load()
+        self.layers = []
+        for L in layers:
+            w = L["weight"].detach()
+            _need(w, "weight")
+            co, ci = int(w.shape[0]), int(w.shape[1])
+            if tuple(w.shape[2:]) != (3, 3, 3) or co > 32 or ci > 32:
+                raise ValueError("the tensor-core path is built for 3x3x3 filters and at most 32 channels")
+            bn = L.get("bn")
+            scale = shift = gamma = beta = None
+            eps = 0.0
+            batch_stats = False
+            if bn is not None:
+                batch_stats = bool(bn["batch_stats"])
+                eps = float(bn["eps"])
+                g = bn["gamma"].detach().float() if bn.get("gamma") is not None else torch.ones(co, device=w.device)
+                b = bn["beta"].detach().float() if bn.get("beta") is not None else torch.zeros(co, device=w.device)
+                if batch_stats:
+                    gamma, beta = _pad32(g, 1.0), _pad32(b, 0.0)
+                else:
+                    sc = g.double() / torch.sqrt(bn["var"].detach().double() + eps)
+                    scale = sc.float().contiguous()
+                    shift = _pad32((b.double() - bn["mean"].detach().double() * sc).float(), 0.0)
+            hi = torch.empty((27, 32, 32), device=w.device, dtype=torch.float32)
+            lo = torch.empty_like(hi)
+            _lib.check(lib.dpv_conv3d_pack_weights(_p(w.contiguous().float()), _p(scale), _p(hi), _p(lo), co, ci, _stream()))
+            self.layers.append(dict(w=(hi, lo), shift=shift, gamma=gamma, beta=beta, eps=eps, batch_stats=batch_stats,
+                                    relu=bool(L.get("relu", False)), block=L.get("block"), co=co, ci=ci))
+        if self.layers[-1]["co"] != 1:
+            raise ValueError("the last layer must be the 32 -> 1 classifier")
+        self._buf = None
+
+    @classmethod
+    def from_module(cls, m):
+        """m: a Base3D (the reference's or the mirror's): dres0, dres_modules (a plain list), classify."""
+        def bn_of(bn):
+            use_batch = bn.training or not bn.track_running_stats
+            return dict(gamma=bn.weight, beta=bn.bias, mean=bn.running_mean, var=bn.running_var, eps=bn.eps,
+                        batch_stats=use_batch)
+        L = [dict(weight=m.dres0[0][0].weight, bn=bn_of(m.dres0[0][1]), relu=True),
+             dict(weight=m.dres0[2][0].weight, bn=bn_of(m.dres0[2][1]), relu=True)]
+        for blk in m.dres_modules:
+            L.append(dict(weight=blk[0][0].weight, bn=bn_of(blk[0][1]), relu=True, block="in"))
+            L.append(dict(weight=blk[2][0].weight, bn=bn_of(blk[2][1]), relu=False, block="out"))
+        L.append(dict(weight=m.classify[0][0].weight, bn=bn_of(m.classify[0][1]), relu=True))
+        L.append(dict(weight=m.classify[2].weight, bn=None, relu=False))
+        return cls(L)
+
+    def __call__(self, volume, out=None):
+        _need(volume, "volume")
+        volume = volume.contiguous()
+        B, C, D, H, W = volume.shape
+        if C != self.layers[0]["ci"]:
+            raise ValueError("volume has %d channels, the first layer takes %d" % (C, self.layers[0]["ci"]))
+        lib = _lib.load()
+        n = int(lib.dpv_conv3d_packed_floats(B, D, H, W))
+        key = (B, D, H, W, str(volume.device))
+        if self._buf is None or self._buf[0] != key:
+            mk = lambda: torch.empty((n,), device=volume.device, dtype=torch.float32)
+            need_raw = any(L["batch_stats"] for L in self.layers)
+            self._buf = (key, [(mk(), mk()) for _ in range(3)], mk() if need_raw else None,
+                         torch.zeros((len(self.layers), 64), device=volume.device, dtype=torch.float64))
+        _, bufs, raw, stats = self._buf
+        st = _stream()
+        if raw is not None:
+            stats.zero_()
+        cur = bufs[0]
+        _lib.check(lib.dpv_conv3d_pack(_p(volume), _p(cur[0]), _p(cur[1]), B, C, D, H, W, st))
+        out = torch.empty((B, D, H, W), device=volume.device, dtype=torch.float32) if out is None else out
+        skip = None
+        for i, L in enumerate(self.layers):
+            last = i == len(self.layers) - 1
+            if L["block"] == "in":
+                skip = cur                         # the block's input: kept until the block's last layer adds it
+            res = skip if L["block"] == "out" else None
+            dst = (None, None) if last else next(b for b in bufs if b is not cur and b is not skip)
+            hi, lo = L["w"]
+            if L["batch_stats"]:
+                _lib.check(lib.dpv_conv3d_c32(_p(cur[0]), _p(cur[1]), _p(hi), _p(lo), None, None, None, None, None, None,
+                                              _p(raw), stats[i].data_ptr(), B, D, H, W, 0, L["ci"], st))
+                _lib.check(lib.dpv_conv3d_bn_apply(_p(raw), stats[i].data_ptr(), _p(L["gamma"]), _p(L["beta"]), L["eps"],
+                                                   _p(res[0]) if res else None, _p(res[1]) if res else None,
+                                                   _p(dst[0]), _p(dst[1]), B, D, H, W, 1 if L["relu"] else 0, st))
+            else:
+                _lib.check(lib.dpv_conv3d_c32(_p(cur[0]), _p(cur[1]), _p(hi), _p(lo), _p(L["shift"]),
+                                              _p(res[0]) if res else None, _p(res[1]) if res else None,
+                                              _p(dst[0]), _p(dst[1]), _p(out) if last else None, None, None,
+                                              B, D, H, W, 1 if L["relu"] else 0, L["ci"], st))
+            if L["block"] == "out":
+                skip = None
+            cur = dst
+        return out
+
+
+def _pad32(t, fill):
+    """A per-channel vector padded to the kernels' 32 channels."""
+    out = torch.full((32,), float(fill), device=t.device, dtype=torch.float32)
+    out[:t.numel()] = t.float()
+    return out
+
+
 # ----------------------------------------------------------------------------- K2b
 def correlation(x1, x2, max_displacement=4):
     """Local correlation [B,(2r+1)^2,H,W] (reference models/correlation_native.py:13-23)."""

@@ -274,3 +274,20 @@ def lidar_case(name):
 
 
 LIDAR_CASES = ["small", "kitti", "sparse"]
+
+
+def base3d_layers(g, T=None):
+    """Layer specs of the Base3D golden (base3d.npz) in the form oracle.dpv_oracle.base3d and ops.Base3DConvs take.
+    T: array -> tensor (default torch.from_numpy)."""
+    import torch
+    T = T or torch.from_numpy
+    relu = [True, True, True, False, True, False, True, False]
+    block = [None, None, "in", "out", "in", "out", None, None]
+    layers = []
+    for i in range(8):
+        bn = None
+        if ("gamma%d" % i) in g:
+            bn = dict(gamma=T(g["gamma%d" % i]), beta=T(g["beta%d" % i]), mean=T(g["mean%d" % i]), var=T(g["var%d" % i]),
+                      eps=float(g["eps%d" % i]), batch_stats=bool(int(g["batch%d" % i])))
+        layers.append(dict(weight=T(g["w%d" % i]), bn=bn, relu=relu[i], block=block[i]))
+    return layers

@@ -539,3 +539,54 @@ def test_cost_refine_vs_reference_golden(dpv):
     logclose(bv, g["bv"])
     want, _ = O.cost_refine(T(g["cost"]), [T(g["w%d" % i]) for i in range(3)], [T(g["b%d" % i]) for i in range(3)], float(g["slope"]))
     logclose(bv, want.float().numpy())
+
+
+# ------------------------------------------------------------------ 8f rank 2, second half: Base3D
+def test_base3d_vs_reference_golden(dpv):
+    """The tcgen05 3-D convolution stack against the reference's own Base3D module (fixture base3d.npz: fp32 CPU,
+    eval(): dres0 / classify on running statistics, the unregistered residual blocks on batch statistics)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "base3d.npz"))
+    net = dpv.ops.Base3DConvs(cases.base3d_layers(g, cu))
+    got = net(cu(g["volume"]))
+    scale = float(np.abs(g["resi"]).max())
+    err = float(np.abs(got.cpu().numpy() - g["resi"]).max()) / scale
+    print("Base3D vs the reference module: max error %.2e of the residual's scale %.1f" % (err, scale))
+    assert err <= 2e-5
+    want = O.base3d(T(g["volume"]), cases.base3d_layers(g))
+    assert float((got.cpu().double() - want).abs().max()) <= 2e-5 * scale
+    # the residual's use (models/models.py:693-694): log_softmax(BV_cur + BV_resi) within the DPV tolerance
+    bv = torch.log_softmax(T(g["volume"])[:, 0], dim=1)
+    upd_want = torch.log_softmax(bv.double() + want, dim=1)
+    upd_got = torch.log_softmax(bv.double() + got.cpu().double(), dim=1)
+    assert float(((upd_got - upd_want).abs() / upd_want.abs().clamp_min(1.0)).max()) <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 8, 9, 11), (2, 4, 16, 12, 20), (1, 4, 3, 5, 130)])
+def test_base3d_tensor_core_vs_oracle(dpv, shape):
+    """Other volume shapes (odd sizes, rows longer than a tile, two items sharing the batch statistics) against the
+    float64 oracle, with the golden's parameters."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "base3d.npz"))
+    net = dpv.ops.Base3DConvs(cases.base3d_layers(g, cu))
+    gen = torch.Generator().manual_seed(sum(shape))
+    vol = torch.randn(shape, generator=gen)
+    want = O.base3d(vol, cases.base3d_layers(g))
+    got = net(vol.cuda()).cpu().double()
+    scale = float(want.abs().max())
+    err = float((got - want).abs().max()) / scale
+    print("Base3D %s: max error %.2e of the residual's scale %.1f" % (shape, err, scale))
+    assert err <= 2e-5
+    again = net(vol.cuda()).cpu().double()          # buffers and statistics are reused call after call
+    assert float((again - want).abs().max()) <= 2e-5 * scale
+
+
+def test_base3d_all_running_statistics(dpv):
+    """Every BatchNorm folded into its convolution (a registered, eval-mode stack; bn_avg: true)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "base3d.npz"))
+    spec, spec_cu = cases.base3d_layers(g), cases.base3d_layers(g, cu)
+    for L in spec + spec_cu:
+        if L["bn"] is not None:
+            L["bn"]["batch_stats"] = False
+    vol = torch.randn((1, 4, 6, 7, 9), generator=torch.Generator().manual_seed(9))
+    want = O.base3d(vol, spec)
+    got = dpv.ops.Base3DConvs(spec_cu)(vol.cuda()).cpu().double()
+    assert float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())

@@ -166,3 +166,16 @@ def test_cost_refine_oracle_vs_the_reference_models_modules():
     assert float((logits - T(g["logits"]).double()).abs().max()) <= 2e-6 * scale      # fp32 summation noise of the reference
     # (1.1e-5 measured: the fp32 convolutions of the reference's CPU build against float64)
     assert float(((bv - T(g["bv"]).double()).abs() / T(g["bv"]).double().abs().clamp_min(1.0)).max()) <= 3e-5
+
+
+def test_base3d_oracle_vs_the_reference_module():
+    """SURVEY 8f rank 2, second half: the oracle's Base3D (float64) against the reference's own Base3D module run in
+    fp32 on the CPU (tests/golden/base3d.npz, make_golden_base3d.py) -- including the four BatchNorms of the
+    unregistered residual blocks, which normalise with batch statistics even after eval()."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "base3d.npz"))
+    layers = cases.base3d_layers(g)
+    assert [bool(L["bn"] and L["bn"]["batch_stats"]) for L in layers] == [False, False, True, True, True, True, False, False]
+    got = O.base3d(torch.from_numpy(g["volume"]), layers)
+    scale = float(np.abs(g["resi"]).max())
+    assert tuple(got.shape) == g["resi"].shape
+    assert float((got - torch.from_numpy(g["resi"]).double()).abs().max()) <= 1e-5 * scale   # fp32 noise of the reference

@@ -345,6 +345,27 @@ def test_cost_refine_convs_vs_the_reference_models_own_modules(dpv, ref):
     assert entry["max_top2_margin_at_flips"] <= 2 * TOL * max(1.0, scale * 1e-2), entry
 
 
+def test_base3d_vs_the_reference_models_own_module(dpv, ref):
+    """SURVEY 8f rank 2, second half, inside the reference model: the volume the feedback model fed to its Base3D
+    (models/models.py:692-693) and what that module returned (cuDNN fp32, TF32 off; BatchNorms as the model holds them),
+    against the tcgen05 stack built from the module (`Base3DConvs.from_module`) on the same tensor."""
+    model = ref_model(ref, "feedback_mono")
+    seen = {}
+    h = model.based_3d.register_forward_hook(lambda m, i, o: seen.update(vol=i[0].detach().clone(), resi=o.detach().clone()))
+    try:
+        run_chain(model, "feedback_mono", 2, 1)                 # the second frame has a real prev_output
+    finally:
+        h.remove()
+    with torch.no_grad():
+        net = dpv.ops.Base3DConvs.from_module(model.based_3d)
+        got = net(seen["vol"].contiguous())
+    scale = float(seen["resi"].abs().max())
+    e = float((got - seen["resi"]).abs().max()) / scale
+    REPORT["site/feedback_mono/based_3d"] = {"residual_scale": scale, "max_error_over_scale": e,
+                                             "batch_stat_layers": sum(1 for L in net.layers if L["batch_stats"])}
+    assert e <= 1e-4, (e, scale)
+
+
 # ---------------------------------------------------------------------------- function level
 def test_hot_path_functions_reference_on_cuda_vs_ours(dpv, ref):
     """Each reference function of SURVEY.md 8a on cuda:0 (torch-CUDA grid_sample / softmax, whose fp32

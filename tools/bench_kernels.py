@@ -191,6 +191,31 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = False
         for k in ("refine_tcgen05_tf32x3", "refine_torch_cudnn_fp32", "refine_torch_cudnn_tf32"):
             print("%-26s %8.4f ms  %6.1f TFLOP/s (conv flops of the three layers)" % (k, res[k]["ms"], res[k]["TFLOPs"]))
+    if want("base3d") and args.only:          # (only on request: 3 GB of buffers, ~100 ms per cuDNN pass)
+        # SURVEY 8f rank 2, second half: Base3D(4, dres_count=2, feature_dim=32) on [Bv, 4, 64, 64, 96]
+        import importlib as _il
+        M = _il.import_module("probabilistic-depth_b200.models.models")
+        Bv = int(os.environ.get("BASE3D_B", "2"))
+        net = M.Base3D(4, dres_count=2, feature_dim=32, bn_running_avg=True).cuda().eval()
+        net.dres_modules = [b.cuda() for b in net.dres_modules]
+        vols = [torch.randn((Bv, 4, D, h, w), device="cuda") for _ in range(2)]
+        flops = 2.0 * Bv * D * h * w * 27 * (4 * 32 + 6 * 32 * 32 + 32)
+        with torch.no_grad():
+            tc = ops.Base3DConvs.from_module(net)
+            med, best = timeit(lambda i: tc(vols[i]), 2, iters=5)
+            res["base3d_tcgen05_tf32x3"] = dict(ms=med, best_ms=best, GBs=0.0, frac=0.0, TFLOPs=flops / med / 1e9)
+            os.environ["DPV_BASE3D_TC"] = "0"
+            for tf32 in (False, True):
+                torch.backends.cudnn.allow_tf32 = tf32
+                for _ in range(2):
+                    net(vols[0])
+                med, best = timeit(lambda i: net(vols[i]), 2, iters=5)
+                res["base3d_torch_cudnn_%s" % ("tf32" if tf32 else "fp32")] = dict(ms=med, best_ms=best, GBs=0.0, frac=0.0,
+                                                                                  TFLOPs=flops / med / 1e9)
+            torch.backends.cudnn.allow_tf32 = False
+            os.environ.pop("DPV_BASE3D_TC")
+        for k in ("base3d_tcgen05_tf32x3", "base3d_torch_cudnn_fp32", "base3d_torch_cudnn_tf32"):
+            print("%-26s %8.4f ms  %6.1f TFLOP/s (conv flops of the eight layers, batch %d)" % (k, res[k]["ms"], res[k]["TFLOPs"], Bv))
     if want("corr"):
         x1 = [torch.randn((2, 32, 96, 208), device="cuda") for _ in range(nrot)]
         x2 = [torch.randn((2, 32, 96, 208), device="cuda") for _ in range(nrot)]
