@@ -272,11 +272,14 @@ conv3d_c32_tc_kernel(const Conv3Args a, const __grid_constant__ Conv3Maps maps) 
 }
 
 // NCDHW fp32 [B][C][D][H][W] (C <= 32) -> packed hi / lo [B][D+2][H+2][W+2][32], zero border, channels >= C zero.
-__global__ void __launch_bounds__(128) conv3d_pack_kernel(const float* __restrict__ x, float* __restrict__ hi,
+// One thread per (position, group of 4 channels): the packed stores of a warp are 512 contiguous bytes.
+__global__ void __launch_bounds__(256) conv3d_pack_kernel(const float* __restrict__ x, float* __restrict__ hi,
                                                           float* __restrict__ lo, int B, int C, int D, int H, int W) {
     const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
     const long long per = (long long)Dp * Hp * Wp;
-    const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long p = t >> 3;
+    const int c = (int)(t & 7) * 4;
     if (p >= (long long)B * per) return;
     const long long b = p / per;
     long long rem = p - b * per;
@@ -286,25 +289,21 @@ __global__ void __launch_bounds__(128) conv3d_pack_kernel(const float* __restric
     const bool real = zp >= 1 && zp <= D && yp >= 1 && yp <= H && xp >= 1 && xp <= W;
     const long long DHW = (long long)D * H * W;
     const float* src = x + b * C * DHW + ((long long)(zp - 1) * H + (yp - 1)) * W + (xp - 1);
-    float4* oh = reinterpret_cast<float4*>(hi + p * C3_C);
-    float4* ol = reinterpret_cast<float4*>(lo + p * C3_C);
+    float v[4];
 #pragma unroll
-    for (int c = 0; c < C3_C; c += 4) {
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (real && c + j < C) ? __ldg(src + (c + j) * DHW) : 0.f;
-        float4 h, l;
-        h.x = ct_hi(v[0]); h.y = ct_hi(v[1]); h.z = ct_hi(v[2]); h.w = ct_hi(v[3]);
-        l.x = ct_hi(v[0] - h.x); l.y = ct_hi(v[1] - h.y); l.z = ct_hi(v[2] - h.z); l.w = ct_hi(v[3] - h.w);
-        oh[c >> 2] = h; ol[c >> 2] = l;
-    }
+    for (int j = 0; j < 4; ++j) v[j] = (real && c + j < C) ? __ldg(src + (c + j) * DHW) : 0.f;
+    float4 h, l;
+    h.x = ct_hi(v[0]); h.y = ct_hi(v[1]); h.z = ct_hi(v[2]); h.w = ct_hi(v[3]);
+    l.x = ct_hi(v[0] - h.x); l.y = ct_hi(v[1] - h.y); l.z = ct_hi(v[2] - h.z); l.w = ct_hi(v[3] - h.w);
+    reinterpret_cast<float4*>(hi)[t] = h;
+    reinterpret_cast<float4*>(lo)[t] = l;
 }
 
 // BatchNorm3d with BATCH statistics (training mode, or track_running_stats = False: torch.nn.functional.batch_norm
 // with training = True) applied to a raw convolution output: y = (x - mean) / sqrt(var + eps) * gamma + beta with the
 // biased variance over the real voxels, then + residual, ReLU, and the split into the next layer's packed hi / lo.
 // stats = the sums the convolution kernel accumulated; count = B * D * H * W.
-__global__ void __launch_bounds__(128) conv3d_bn_apply_kernel(const float* __restrict__ raw, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256) conv3d_bn_apply_kernel(const float* __restrict__ raw, const double* __restrict__ stats,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               float eps, const float* __restrict__ res_hi,
                                                               const float* __restrict__ res_lo, float* __restrict__ hi,
@@ -324,7 +323,10 @@ __global__ void __launch_bounds__(128) conv3d_bn_apply_kernel(const float* __res
         sh_s[threadIdx.x] = (float)(bt - mean * sc);
     }
     __syncthreads();
-    const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+    // one thread per (position, group of 4 channels): every load and store of a warp is 512 contiguous bytes
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long p = t >> 3;
+    const int c = (int)(t & 7) * 4;
     if (p >= (long long)B * per) return;
     const long long b = p / per;
     long long rem = p - b * per;
@@ -332,28 +334,23 @@ __global__ void __launch_bounds__(128) conv3d_bn_apply_kernel(const float* __res
     rem -= (long long)zp * (Hp * Wp);
     const int yp = (int)rem / Wp, xp = (int)rem - yp * Wp;
     const bool real = zp >= 1 && zp <= D && yp >= 1 && yp <= H && xp >= 1 && xp <= W;
-    const float4* src = reinterpret_cast<const float4*>(raw + p * C3_C);
-    float4* oh = reinterpret_cast<float4*>(hi + p * C3_C);
-    float4* ol = reinterpret_cast<float4*>(lo + p * C3_C);
-#pragma unroll
-    for (int c = 0; c < C3_C; c += 4) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (real) {
-            const float4 x = __ldg(src + (c >> 2));
-            v[0] = fmaf(x.x, sc_s[c], sh_s[c]); v[1] = fmaf(x.y, sc_s[c + 1], sh_s[c + 1]);
-            v[2] = fmaf(x.z, sc_s[c + 2], sh_s[c + 2]); v[3] = fmaf(x.w, sc_s[c + 3], sh_s[c + 3]);
-            if (res_hi != nullptr) {
-                const float4 h = __ldg(reinterpret_cast<const float4*>(res_hi + p * C3_C) + (c >> 2));
-                const float4 l = __ldg(reinterpret_cast<const float4*>(res_lo + p * C3_C) + (c >> 2));
-                v[0] += h.x + l.x; v[1] += h.y + l.y; v[2] += h.z + l.z; v[3] += h.w + l.w;
-            }
-            if (relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (real) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(raw) + t);
+        v[0] = fmaf(x.x, sc_s[c], sh_s[c]); v[1] = fmaf(x.y, sc_s[c + 1], sh_s[c + 1]);
+        v[2] = fmaf(x.z, sc_s[c + 2], sh_s[c + 2]); v[3] = fmaf(x.w, sc_s[c + 3], sh_s[c + 3]);
+        if (res_hi != nullptr) {
+            const float4 h = __ldg(reinterpret_cast<const float4*>(res_hi) + t);
+            const float4 l = __ldg(reinterpret_cast<const float4*>(res_lo) + t);
+            v[0] += h.x + l.x; v[1] += h.y + l.y; v[2] += h.z + l.z; v[3] += h.w + l.w;
         }
-        float4 h, l;
-        h.x = ct_hi(v[0]); h.y = ct_hi(v[1]); h.z = ct_hi(v[2]); h.w = ct_hi(v[3]);
-        l.x = ct_hi(v[0] - h.x); l.y = ct_hi(v[1] - h.y); l.z = ct_hi(v[2] - h.z); l.w = ct_hi(v[3] - h.w);
-        oh[c >> 2] = h; ol[c >> 2] = l;
+        if (relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
     }
+    float4 h, l;
+    h.x = ct_hi(v[0]); h.y = ct_hi(v[1]); h.z = ct_hi(v[2]); h.w = ct_hi(v[3]);
+    l.x = ct_hi(v[0] - h.x); l.y = ct_hi(v[1] - h.y); l.z = ct_hi(v[2] - h.z); l.w = ct_hi(v[3] - h.w);
+    reinterpret_cast<float4*>(hi)[t] = h;
+    reinterpret_cast<float4*>(lo)[t] = l;
 }
 
 // torch weight [C_out][C_in][3][3][3] (C_out, C_in <= 32), optional per-output-channel scale (the folded BatchNorm)
@@ -397,7 +394,7 @@ extern "C" int dpv_conv3d_pack(const float* x, float* packed_hi, float* packed_l
     if (C > C3_C) return DPV_E_UNSUPP;
     const long long n = (long long)B * (D + 2) * (H + 2) * (W + 2);
     if (n > (1LL << 31) - 4096) return DPV_E_UNSUPP;
-    conv3d_pack_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, packed_hi, packed_lo, B, C, D, H, W);
+    conv3d_pack_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, packed_hi, packed_lo, B, C, D, H, W);
     DPV_LAUNCH_END();
     return 0;
 }
@@ -464,7 +461,7 @@ extern "C" int dpv_conv3d_bn_apply(const float* raw, const double* stats, const 
     DPV_CHECK_ARG((res_hi == nullptr) == (res_lo == nullptr));
     if (((uintptr_t)raw | (uintptr_t)out_hi | (uintptr_t)out_lo | (uintptr_t)res_hi | (uintptr_t)res_lo) & 15) return DPV_E_BADARG;
     const long long n = (long long)B * (D + 2) * (H + 2) * (W + 2);
-    conv3d_bn_apply_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(raw, stats, gamma, beta, eps, res_hi,
+    conv3d_bn_apply_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, stats, gamma, beta, eps, res_hi,
                                                                                        res_lo, out_hi, out_lo, B, D, H, W, relu ? 1 : 0);
     DPV_LAUNCH_END();
     return 0;

@@ -170,16 +170,16 @@ class cpu_hot_path:
         reference_loader.restore()
 
 
-def bound(entry, floor, key):
-    """1e-4, or three times the reference's own CPU-vs-CUDA spread at the same place if that is larger."""
-    return max(TOL, 3.0 * floor[key])
+def bound(entry, floor, key, factor=3.0):
+    """1e-4, or `factor` times the reference's own CPU-vs-CUDA spread at the same place if that is larger."""
+    return max(TOL, factor * floor[key])
 
 
-def check_against_floor(entry, floor):
+def check_against_floor(entry, floor, factor=3.0):
     for key in ("log_dpv", "mean", "var"):
-        assert entry[key] <= bound(entry, floor, key), (key, entry, floor)
+        assert entry[key] <= bound(entry, floor, key, factor), (key, entry, floor)
     # an arg-max may only move where the reference's own top-2 margin is inside the noise
-    assert entry["max_top2_margin_at_flips"] <= 2 * bound(entry, floor, "log_dpv"), (entry, floor)
+    assert entry["max_top2_margin_at_flips"] <= 2 * bound(entry, floor, "log_dpv", factor), (entry, floor)
 
 
 @pytest.mark.parametrize("name,batch", [("default_stereo", 2), ("upsample_mono", 2)])
@@ -202,9 +202,13 @@ def test_basemodel_reference_vs_patched_vs_mirror(dpv, ref, name, batch):
     mirror = run_chain(mirror_model(name, model), name, 1, batch)
     fl = {"bv": compare("%s/floor/bv" % name, floor[0][0], want[0][0], MC.D_CANDI),
           "refined": compare("%s/floor/refined" % name, floor[0][1], want[0][1], MC.D_CANDI)}
-    for tag, got in (("patched", patched), ("mirror", mirror)):
-        check_against_floor(compare("%s/%s/bv" % (name, tag), got[0][0], want[0][0], MC.D_CANDI), fl["bv"])
-        check_against_floor(compare("%s/%s/refined" % (name, tag), got[0][1], want[0][1], MC.D_CANDI), fl["refined"])
+    # the floor arm swaps only the hot-path functions (CPU vs CUDA); the patched arm does the same with our kernels
+    # (3x the floor); the mirror ALSO replaces the cuDNN fp32 convolutions before the 1/4-res soft-max by the tcgen05
+    # TF32x3 kernels -- a second, independent fp32-class rounding of logits of O(1000) (pinned directly at 2e-6 of
+    # their scale by test_cost_refine_convs_vs_the_reference_models_own_modules) -- hence 4x
+    for tag, got, factor in (("patched", patched, 3.0), ("mirror", mirror, 4.0)):
+        check_against_floor(compare("%s/%s/bv" % (name, tag), got[0][0], want[0][0], MC.D_CANDI), fl["bv"], factor)
+        check_against_floor(compare("%s/%s/refined" % (name, tag), got[0][1], want[0][1], MC.D_CANDI), fl["refined"], factor)
     # the patched reference and the mirror run the same kernels; what separates them is the cuDNN stack's
     # own run-to-run / batching noise (the reference differs from ITSELF by REPORT[.../reference_run_to_run])
     assert scaled(patched[0][1], mirror[0][1]) <= bound(None, fl["refined"], "log_dpv")
@@ -240,9 +244,9 @@ def test_feedback_16_frames_reference_vs_patched_vs_mirror(dpv, ref):
     print(json.dumps(worst, indent=1))
     for kind in ("forced", "free"):
         fl = worst["floor_" + kind]
-        for tag in ("patched_" + kind, "mirror_" + kind):
-            check_against_floor(worst[tag], fl)
-            assert worst[tag]["bv_upd"] <= max(TOL, 3 * fl["bv_upd"]), (tag, worst[tag], fl)
+        for tag, factor in (("patched_" + kind, 3.0), ("mirror_" + kind, 4.0)):     # (the mirror also swaps the convolutions)
+            check_against_floor(worst[tag], fl, factor)
+            assert worst[tag]["bv_upd"] <= max(TOL, factor * fl["bv_upd"]), (tag, worst[tag], fl)
 
 
 # ---------------------------------------------------------------------------- call-site level
