@@ -176,6 +176,17 @@ def reference_step_fn(dpv, wl, frames, device):
             kw = dict(mode="upsample", dmaps=t["dmaps"], masks=t["masks"])
         elif mode == "feedback":
             kw = dict(mode="feedback", feat_raw=t["feat_raw"], bv_resi=t["bv_resi"])
+        if wl.get("refine"):
+            # the model's own 1/4-res head modules (models/models.py:456-460), random-init as the model builds them
+            M = ref.models
+            torch.manual_seed(7)
+            mods = torch.nn.Sequential(M.conv2d_leakyRelu(wl["D"], wl["D"], 3, 1, 1), M.conv2d_leakyRelu(wl["D"], wl["D"], 3, 1, 1),
+                                       torch.nn.Conv2d(wl["D"], wl["D"], 3, 1, 1)).to(device).eval()
+
+            def refine_ref(c):
+                with torch.no_grad():
+                    return mods(c)
+            kw["refine"] = refine_ref
         return (lambda: reference_frame.frame_hot_path(ref, t["feats"], t["poses"], t["K"], t["rays"], hi["d"], 10.0,
                                                        t["logits"], t["intr_up"], want=False, **kw)), "reference"
     # no reference tree on this machine: the restatement (CPU only, default frame)
@@ -556,7 +567,8 @@ def run_ours(args, dpv, wl):
     bound_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     e2e_steps = max(4, min(args.steps, 30))
     pipe = None
-    if mode == "default":
+    # (the C pipeline has no convolution stage: the refine workload goes through FrameStep.run between pinned copies)
+    if mode == "default" and not wl.get("refine"):
         pipe = pipe_mod.FramePipeline(B, wl["V"], wl["C"], wl["D"], wl["h"], wl["w"], wl["H"], wl["W"], device=local)
         pins = [{k: torch.from_numpy(np.ascontiguousarray(h_[k])).pin_memory()
                  for k in ("feats", "poses", "K", "rays", "logits", "intr_up")}

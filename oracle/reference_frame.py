@@ -53,14 +53,15 @@ def head_batch(ref, logits_full, d_candi, intr_up, uf=True):
 
 
 def frame_hot_path(ref, feats, poses, K, rays, d_candi, sigma, logits_full, intr_up, mode="default",
-                   dmaps=None, masks=None, feat_raw=None, bv_resi=None, want=True):
+                   dmaps=None, masks=None, feat_raw=None, bv_resi=None, want=True, refine=None):
     """feats [B,V+1,C,h,w] (reference view last), poses [B,V+1,4,4], K [B,3,3], rays [B,3,h*w],
     logits_full [B,D,H,W], intr_up [B,3,3]; d_candi numpy float64 [D].  mode "upsample": dmaps [B,h,w],
     masks [B,1,h,w]; mode "feedback": feat_raw [B,V+1,D,h,w], bv_resi [B,D,h,w].  Returns a dict of batched
-    results (or nothing when want=False: timing only)."""
+    results (or nothing when want=False: timing only).  refine: optional callable cost -> logits (the model's
+    conv0 / conv0_1 / conv0_2 modules, models/models.py:555-557) applied before the 1/4-res soft-max."""
     hom, iu = ref.homography, ref.img_utils
     cost = sweep_batch(ref, feats, poses, K, rays, d_candi, sigma)
-    bv = F.log_softmax(cost, dim=1)                                             # models.py:560 / packnet.py:394
+    bv = F.log_softmax(cost if refine is None else refine(cost), dim=1)         # models.py:560 / packnet.py:394
     extra = {}
     if mode == "upsample":                                                      # models.py:666-672
         prior = iu.gen_dpv_withmask(dmaps, masks, d_candi, 0.3)

@@ -28,8 +28,10 @@
 //     epilogue of a tile overlaps the copies and MMAs of the next.  Measured on the way (B=8, 64x96, three layers
 //     + pack, graph-timed): one tile per CTA 0.1245 ms -> persistent + double-buffered 0.0982 -> N = 128 MMAs
 //     0.0857.  Timing experiments on the one-tile kernel: without the copies after the first two K-blocks 0.1230
-//     (copies were hidden), without the MMAs 0.0794 (= copies + epilogues: 202 MB per layer from L2 into shared
-//     memory in ~23 us, about 0.7 of the chip's L2 throughput); at 0.0857 the kernel sits on that L2 -> SM floor.
+//     (copies were hidden), without the MMAs 0.0794 (= copies + epilogues).  ncu of the persistent kernel: tensor
+//     pipe busy 55-62 % of the SM-active time (an M = 128, K = 8 TF32 MMA occupies it ~50 cycles at N <= 64, ~64 at
+//     N = 128), 204 MB per layer from L2 at 7 TB/s underneath, a quarter of the launch ramp and tail (405 tiles on
+//     148 SMs).
 //   * Warp roles: warp 0 = TMA producer (per K-block A_hi, A_lo and W_hi / W_lo of three taps; 82 KB per stage, 2 stages),
 //     warp 1 = TMEM allocation + MMA issue (tcgen05.commit releases a stage / publishes the accumulators),
 //     warps 2-5 = epilogue: tcgen05.ld gives every thread ONE pixel with all 64 output channels in registers, so

@@ -13,12 +13,15 @@ for w in feedback upsample stress large_d stereo_refine; do
   python bench.py --workload $w --steps 50 > $O/bench_$w.json 2> $O/bench_$w.err; echo "$w rc=$?"; tail -2 $O/bench_$w.err
 done
 python tools/bench_kernels.py --graph > $O/kernels_graph.log 2>&1; grep -v "^{" $O/kernels_graph.log
+for b in 2 8; do BASE3D_B=$b python tools/bench_kernels.py --only base3d 2>&1 | grep -v "^{" | tail -3; done > $O/base3d.log; cat $O/base3d.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/launches_bench.log 2>&1; echo "ncu launch list rc=$?"
 N=3 ncu --set full --clock-control none --import-source on -k regex:"sweep_xcorr|sweep_smaps|head_uf_tile" -s 5 -c 4 \
     -o $O/prof_step python tools/run_once.py > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"conv3x3" -s 4 -c 4 \
     -o $O/prof_conv python tools/bench_kernels.py --only refine > $O/ncu_conv.log 2>&1; echo "ncu conv rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:"conv3d_c32|conv3d_bn" -s 11 -c 4 \
+    -o $O/prof_conv3d python tools/run_base3d.py > $O/ncu_conv3d.log 2>&1; echo "ncu conv3d rc=$?"
 compute-sanitizer --tool memcheck python tools/run_small_step.py > $O/sanitizer_memcheck.log 2>&1; tail -3 $O/sanitizer_memcheck.log
 compute-sanitizer --tool racecheck python tools/run_small_step.py > $O/sanitizer_racecheck.log 2>&1; tail -3 $O/sanitizer_racecheck.log
 python - <<'PY'

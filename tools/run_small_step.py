@@ -3,7 +3,7 @@
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 dpv = importlib.import_module("probabilistic-depth_b200")
 frame = importlib.import_module("probabilistic-depth_b200.frame")
 s = dpv.synth
@@ -38,6 +38,12 @@ bs = [cu(0.1 * s.randn(30 + i, 64)) for i in range(3)]
 lp = dpv.ops.CostRefine(ws, bs)(cu(4 * s.randn(40, 2, 64, 16, 24) + 10))
 torch.cuda.synchronize()
 print("refine ok", float(torch.logsumexp(lp, 1).abs().max()))
+# the 3-D convolution stack (Base3D): folded and batch-statistics BatchNorms, residual blocks, 4 -> 32 -> ... -> 1
+import cases
+g3 = np.load(os.path.join(ROOT, "tests", "golden", "base3d.npz"))
+resi = dpv.ops.Base3DConvs(cases.base3d_layers(g3, cu))(cu(g3["volume"]))
+torch.cuda.synchronize()
+print("base3d ok", float(np.abs(resi.cpu().numpy() - g3["resi"]).max()))
 a = cu(np.abs(s.randn(8, 2, 32, 48)) + 1)
 dpv.ops.depth_errors(a, a * 1.1)
 torch.cuda.synchronize()
