@@ -11,6 +11,9 @@ Workloads (BASELINE.json configs; D=64 bins, image 256x384, features / cost volu
            3x3 convolutions on the tcgen05 tensor cores, random-init weights.
   feedback (configs[2]) default_mono_feedback: + feedback warp of the previous DPV and log_softmax(BV + resi);
            8 sequences per GPU, a step = one frame of every sequence (16 steps = the 16-frame sequence).
+  feedback_refine  the same with the model's Base3D inside the step (second half): the residual is
+           computed from cat(BV, prev_output, warped features) by the 3-D convolution stack on the tcgen05 tensor
+           cores instead of being a synthetic input; every arm (ours, incumbent, CPU reference) runs it.
   upsample (configs[3]) default_mono_upsample: + LiDAR prior and Bayesian fusion; GLOBAL batch 32 split over
            the ranks ("strong" scaling).
   stress   north_star's literal shape: cost volume + soft-max head directly on 256x384 features, C=67
@@ -57,6 +60,10 @@ WORKLOADS = {
     "feedback": dict(BASE, B=8, mode="feedback", pose="mono", scaling="weak",
                      desc="default_mono_feedback: 8 sequences/GPU, one frame of each per step (16 steps = the 16-frame "
                           "sequence), feedback warp + fusion, D=64, image 256x384, features 64x96, C=67, V=1"),
+    "feedback_refine": dict(BASE, B=8, mode="feedback", pose="mono", scaling="weak", base3d=True,
+                            desc="default_mono_feedback with the model's Base3D in the step: cost volume -> warp_feature -> "
+                                 "Base3D(cat(BV, prev, warped)) (tcgen05, TF32x3; residual blocks on batch statistics as in "
+                                 "the reference) -> log_softmax(BV + resi) -> full-res head + UF; 8 sequences/GPU, D=64, 256x384"),
     "upsample": dict(BASE, B=32, mode="upsample", pose="stereo", scaling="strong",
                      desc="default_mono_upsample: global batch 32 split over the GPUs, sparse depth prior + Bayesian "
                           "fusion, D=64, image 256x384, features 64x96, C=67, V=1"),
@@ -92,11 +99,16 @@ def host_inputs(dpv, wl, batch, seed=0):
         out["dmaps"], out["masks"] = s.sparse_depth(seed + 3, batch, wl["h"], wl["w"])
     if wl["mode"] == "feedback":
         out["feat_raw"] = s.randn(seed + 4, batch, wl["V"] + 1, wl["D"], wl["h"], wl["w"])
-        out["bv_resi"] = 0.5 * s.randn(seed + 5, batch, wl["D"], wl["h"], wl["w"])
+        if wl.get("base3d"):       # the previous frame's 1/4-res hand-off (a log-DPV); the residual is computed in the step
+            z = 2.0 * s.randn(seed + 5, batch, wl["D"], wl["h"], wl["w"])
+            z = z - z.max(axis=1, keepdims=True)
+            out["prev"] = (z - np.log(np.exp(z).sum(axis=1, keepdims=True))).astype(np.float32)
+        else:
+            out["bv_resi"] = 0.5 * s.randn(seed + 5, batch, wl["D"], wl["h"], wl["w"])
     return out
 
 
-TENSOR_KEYS = ("feats", "poses", "K", "rays", "logits", "intr_up", "dmaps", "masks", "feat_raw", "bv_resi")
+TENSOR_KEYS = ("feats", "poses", "K", "rays", "logits", "intr_up", "dmaps", "masks", "feat_raw", "bv_resi", "prev")
 
 
 class ClockSampler(threading.Thread):
@@ -150,6 +162,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def base3d_module(dpv, wl, device, models=None):
+    """Base3D as the feedback model builds it (models/models.py:464), random init, eval(): dres0 / classify on their
+    running statistics, the unregistered residual blocks on batch statistics.  models: the module that defines Base3D
+    (default: our mirror; the reference arms pass the reference's)."""
+    import importlib
+    M = models or importlib.import_module("probabilistic-depth_b200.models.models")
+    torch.manual_seed(11)
+    real_cuda = torch.nn.Module.cuda
+    if str(device) == "cpu":
+        torch.nn.Module.cuda = lambda self, device=None: self      # the reference's __init__ calls .cuda() on the blocks
+    try:
+        net = M.Base3D(wl["V"] + 3, dres_count=2, feature_dim=32, bn_running_avg=True, id=0)
+    finally:
+        torch.nn.Module.cuda = real_cuda
+    net = net.to(device).eval()
+    net.dres_modules = [b.to(device) for b in net.dres_modules]
+    return net
+
+
 # ------------------------------------------------------------------------------------ reference arms
 def reference_step_fn(dpv, wl, frames, device):
     """A closure running `frames` frames of `wl` through the reference's own functions on `device`
@@ -175,7 +206,14 @@ def reference_step_fn(dpv, wl, frames, device):
         if mode == "upsample":
             kw = dict(mode="upsample", dmaps=t["dmaps"], masks=t["masks"])
         elif mode == "feedback":
-            kw = dict(mode="feedback", feat_raw=t["feat_raw"], bv_resi=t["bv_resi"])
+            kw = dict(mode="feedback", feat_raw=t["feat_raw"], bv_resi=t.get("bv_resi"))
+            if wl.get("base3d"):
+                net = base3d_module(dpv, wl, device, models=ref.models)
+
+                def base3d_ref(vol):
+                    with torch.no_grad():
+                        return net(vol, prob=False)
+                kw.update(prev=t["prev"], base3d=base3d_ref)
         if wl.get("refine"):
             # the model's own 1/4-res head modules (models/models.py:456-460), random-init as the model builds them
             M = ref.models
@@ -419,15 +457,18 @@ def run_ours(args, dpv, wl):
             std = (2.0 / (9 * 64)) ** 0.5                       # models/models.py weight_init
             refine = dpv.ops.CostRefine([torch.randn((64, 64, 3, 3), device=dev, generator=gw) * std for _ in range(3)],
                                         [torch.randn((64,), device=dev, generator=gw) * 0.1 for _ in range(3)])
+        base3d = None
+        if wl.get("base3d"):
+            base3d = dpv.ops.Base3DConvs.from_module(base3d_module(dpv, wl, dev))
         step = frame_mod.FrameStep(B, wl["V"], wl["C"], wl["D"], wl["h"], wl["w"], wl["H"], wl["W"], hi["d"],
                                    sigma=10.0, mode=mode, device=dev, fuse_uf=not args.no_fuse_uf,
-                                   fuse_lsm=not args.no_fuse_lsm, refine=refine)
+                                   fuse_lsm=not args.no_fuse_lsm, refine=refine, base3d=base3d)
         nset = 2 if B <= 16 else 1
         dsets = [to_dev(hi if i == 0 else host_inputs(dpv, wl, B, seed=rank + 1000 * i)) for i in range(nset)]
 
         def run_step(s, **kw):
             step.run(s["feats"], s["poses"], s["K"], s["rays"], s["logits"], s["intr_up"], dmaps=s.get("dmaps"),
-                     masks=s.get("masks"), feat_raw=s.get("feat_raw"), bv_resi=s.get("bv_resi"), **kw)
+                     masks=s.get("masks"), feat_raw=s.get("feat_raw"), bv_resi=s.get("bv_resi"), prev=s.get("prev"), **kw)
         results = lambda: frame_results(step)
     elif mode == "stress":
         step = StressStep(dpv, wl, B, hi["d"], dev)

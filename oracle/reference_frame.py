@@ -53,12 +53,15 @@ def head_batch(ref, logits_full, d_candi, intr_up, uf=True):
 
 
 def frame_hot_path(ref, feats, poses, K, rays, d_candi, sigma, logits_full, intr_up, mode="default",
-                   dmaps=None, masks=None, feat_raw=None, bv_resi=None, want=True, refine=None):
+                   dmaps=None, masks=None, feat_raw=None, bv_resi=None, want=True, refine=None, prev=None,
+                   base3d=None):
     """feats [B,V+1,C,h,w] (reference view last), poses [B,V+1,4,4], K [B,3,3], rays [B,3,h*w],
     logits_full [B,D,H,W], intr_up [B,3,3]; d_candi numpy float64 [D].  mode "upsample": dmaps [B,h,w],
     masks [B,1,h,w]; mode "feedback": feat_raw [B,V+1,D,h,w], bv_resi [B,D,h,w].  Returns a dict of batched
     results (or nothing when want=False: timing only).  refine: optional callable cost -> logits (the model's
-    conv0 / conv0_1 / conv0_2 modules, models/models.py:555-557) applied before the 1/4-res soft-max."""
+    conv0 / conv0_1 / conv0_2 modules, models/models.py:555-557) applied before the 1/4-res soft-max.  base3d:
+    optional callable volume -> residual (the model's Base3D, models/models.py:692-693) fed with
+    cat(BV, prev, warped); bv_resi is then ignored."""
     hom, iu = ref.homography, ref.img_utils
     cost = sweep_batch(ref, feats, poses, K, rays, d_candi, sigma)
     bv = F.log_softmax(cost if refine is None else refine(cost), dim=1)         # models.py:560 / packnet.py:394
@@ -75,7 +78,10 @@ def frame_hot_path(ref, feats, poses, K, rays, d_candi, sigma, logits_full, intr
             cam = {"intrinsic_M_cuda": K[i], "intrinsic_M": K[i].cpu().numpy(), "unit_ray_array_2D": rays[i]}
             warped.append(hom.warp_feature(feat_raw[i].unsqueeze(0), d_candi, poses[i, :, :3, :3],
                                            poses[i, :, :3, 3], cam))
-        extra = dict(warped=torch.cat(warped, dim=0), bv_upd=F.log_softmax(bv + bv_resi, dim=1))
+        warped = torch.cat(warped, dim=0)
+        if base3d is not None:                                                  # models.py:692-693
+            bv_resi = base3d(torch.cat([bv.unsqueeze(1), prev.unsqueeze(1), warped], dim=1))
+        extra = dict(warped=warped, bv_upd=F.log_softmax(bv + bv_resi, dim=1))
     out = head_batch(ref, logits_full, d_candi, intr_up)
     if not want:
         return None

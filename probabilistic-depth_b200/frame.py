@@ -19,9 +19,11 @@ from . import _lib, ops
 
 class FrameStep:
     def __init__(self, B, V, C, D, h, w, H, W, d_candi, sigma=10.0, mode="default", device=None,
-                 fuse_uf=True, fuse_lsm=True, refine=None):
+                 fuse_uf=True, fuse_lsm=True, refine=None, base3d=None):
         """refine: optional ops.CostRefine (conv0 -> conv0_1 -> conv0_2 -> log-softmax, models/models.py:555-560):
-        the 1/4-res BV is then the refined cost volume instead of the soft-max of the cost volume itself."""
+        the 1/4-res BV is then the refined cost volume instead of the soft-max of the cost volume itself.
+        base3d: optional ops.Base3DConvs (feedback mode): the residual is then computed in the step from
+        cat(BV, prev_output, warped features) as the model does (models/models.py:692-694) instead of being an input."""
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dev = dev
         self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W = B, V, C, D, h, w, H, W
@@ -59,9 +61,13 @@ class FrameStep:
         if mode == "upsample":
             self.fused = e(B, D, h, w)
             self.logfused = e(B, D, h, w)
+        self.base3d = base3d if mode == "feedback" else None
         if mode == "feedback":
             self.warped = e(B, V + 1, D, h, w)
             self.bv_upd = e(B, D, h, w)
+            if self.base3d is not None:
+                self.comb = e(B, V + 3, D, h, w)
+                self.resi = e(B, D, h, w)
         # scratch of the sweep's cross-correlation form (source-only product maps, one pre-pass per call)
         self.sweep_ws = e(int(self.lib.dpv_sweep_workspace_floats(B, V, h, w)))
         self.sweep_algo = 0
@@ -71,11 +77,12 @@ class FrameStep:
 
     # -- one batch of frames ---------------------------------------------------------------
     def run(self, feats, poses, K, rays, logits_full, intr_up, dmaps=None, masks=None,
-            feat_raw=None, bv_resi=None, head_hook=None, kernel_hook=None):
+            feat_raw=None, bv_resi=None, prev=None, head_hook=None, kernel_hook=None):
         """feats [B,V+1,C,h,w] (reference view last); poses [B,V+1,4,4]; K [B,3,3]; rays
         [B,3,h*w]; logits_full [B,D,H,W] (the decoder's pre-softmax output); intr_up [B,3,3].
         upsample: dmaps [B,h,w], masks [B,1,h,w].  feedback: feat_raw [B,V+1,D,h,w], bv_resi
-        [B,D,h,w] (the 3-D conv residual).  All contiguous fp32 on this device."""
+        [B,D,h,w] (the 3-D conv residual) -- or, with base3d, prev [B,D,h,w] (the previous frame's 1/4-res
+        hand-off) from which the residual is computed here.  All contiguous fp32 on this device."""
         B, V, C, D, h, w, H, W = self.B, self.V, self.C, self.D, self.h, self.w, self.H, self.W
         lib, st = self.lib, torch.cuda.current_stream().cuda_stream
         p = lambda t: None if t is None else t.data_ptr()
@@ -109,6 +116,13 @@ class FrameStep:
                                             p(self.warped), B, V + 1, D, h, w, (V + 1) * 16, 9,
                                             3 * h * w, st))
             hk("warp_feature", 1)
+            if self.base3d is not None:
+                hk("base3d", 0)
+                self.comb[:, 0].copy_(self.bv)                 # models/models.py:692: cat(BV_cur, prev_output, warped)
+                self.comb[:, 1].copy_(prev)
+                self.comb[:, 2:].copy_(self.warped)
+                bv_resi = self.base3d(self.comb, out=self.resi)
+                hk("base3d", 1)
             hk("feedback_fuse", 0)
             _lib.check(lib.dpv_head(p(self.bv), p(bv_resi), p(self.d), p(self.bv_upd), None, None,
                                     None, None, None, B, D, h, w, ops.IN_LOGITS, st))
@@ -223,6 +237,8 @@ class FrameStep:
         if self.mode == "feedback":
             k["warp_feature"] = 8 * hw * D * (V + 1) + 12 * hw
             k["feedback_fuse"] = 12 * hw * D
+            if self.base3d is not None:
+                k["base3d"] = 4 * hw * D * (V + 3) + 4 * hw * D     # the volume in, the residual out (a tensor-pipe stage)
         return {n: v * B for n, v in k.items()}
 
     def sweep_flops(self):

@@ -9,7 +9,7 @@ python -m pytest tests -q -m gpu 2>&1 | tail -3 > $O/pytest_gpu_again.log; tail 
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench rc=$?"; tail -3 $O/bench_n1.err
 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; echo "ref rc=$?"
-for w in feedback upsample stress large_d stereo_refine; do
+for w in feedback upsample stress large_d stereo_refine feedback_refine; do
   python bench.py --workload $w --steps 50 > $O/bench_$w.json 2> $O/bench_$w.err; echo "$w rc=$?"; tail -2 $O/bench_$w.err
 done
 python tools/bench_kernels.py --graph > $O/kernels_graph.log 2>&1; grep -v "^{" $O/kernels_graph.log
@@ -26,7 +26,7 @@ compute-sanitizer --tool memcheck python tools/run_small_step.py > $O/sanitizer_
 compute-sanitizer --tool racecheck python tools/run_small_step.py > $O/sanitizer_racecheck.log 2>&1; tail -3 $O/sanitizer_racecheck.log
 python - <<'PY'
 import json
-for n in ("n1", "feedback", "upsample", "stress", "large_d", "stereo_refine"):
+for n in ("n1", "feedback", "upsample", "stress", "large_d", "stereo_refine", "feedback_refine"):
     try:
         d = json.loads(open("gpurun_out/bench_%s.json" % n).read())
         print(n, "value %.0f  ms %.4f  roofline %.3f (in step %.3f)  frame_hbm %.3f  survey_hbm %.3f  e2e %.0f (%.2f of ceiling)  incumbent %s  cpu %s" % (
