@@ -5,11 +5,13 @@ size-independent properties (normalisation, hand-off identity, uniform-prior inv
 the production sweep kernel with the operation-by-operation one, shard-merge == unsharded).
 """
 import importlib
+import os
 
 import numpy as np
 import pytest
 import torch
 
+import cases
 from oracle import dpv_oracle as O
 from uf_helpers import near_threshold_columns
 
@@ -355,3 +357,34 @@ def test_frame_step_with_the_models_quarter_res_head(dpv):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(step.bv, first)
+
+
+def test_feedback_step_with_base3d_in_the_step(dpv):
+    """FrameStep(mode="feedback", base3d=Base3DConvs): the residual is computed in the step from
+    cat(BV, prev_output, warped features) (models/models.py:692-694) by the tensor-core 3-D convolution stack; checked
+    against the float64 oracle evaluated on the step's own BV and warped features; the step replays from a CUDA graph."""
+    frame = importlib.import_module("probabilistic-depth_b200.frame")
+    s = dpv.synth
+    B, V, C, D, h, w, H, W = 2, 1, 19, 64, 16, 24, 64, 96
+    d = s.depth_candidates(5, 40, D)
+    cam = s.camera(w, h, B)
+    g3 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "base3d.npz"))
+    net = dpv.ops.Base3DConvs(cases.base3d_layers(g3, cu))
+    prev = torch.log_softmax(cu(2.0 * s.randn(9, B, D, h, w)), dim=1)
+    args = (cu(s.randn(1, B, V + 1, C, h, w)), cu(s.mono_poses(B)), cu(cam["intrinsics"]), cu(cam["unit_ray"]),
+            cu(s.ground_plane_logits(2, B, H, W, d, cam["intrinsics_up"][0])), cu(cam["intrinsics_up"]))
+    kw = dict(feat_raw=cu(s.randn(4, B, V + 1, D, h, w)), prev=prev)
+    step = frame.FrameStep(B, V, C, D, h, w, H, W, d, mode="feedback", base3d=net)
+    step.run(*args, **kw)
+    torch.cuda.synchronize()
+    vol = torch.cat([step.bv.unsqueeze(1), prev.unsqueeze(1), step.warped], dim=1).cpu()
+    resi = O.base3d(vol, cases.base3d_layers(g3))
+    assert float((step.resi.cpu().double() - resi).abs().max()) <= 2e-5 * float(resi.abs().max())
+    want = torch.log_softmax(step.bv.cpu().double() + resi, dim=1)
+    assert scaled_err(step.bv_upd, want.float().cuda()) < 1e-4
+    first = step.bv_upd.clone()
+    graph = step.capture(*args, **kw)
+    step.bv_upd.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(step.bv_upd, first)
