@@ -25,7 +25,8 @@ The CNN blocks between the kernels are cuDNN's and are not part of the path (the
 `value`    : frames/s with every input already resident in HBM, device-timed, max over ranks.
 `e2e`      : frames/s through the host-buffer API: pinned host inputs are copied in, results copied back, inside
              the timed region (stereo: dpv_pipeline_submit / _wait, two batches in flight; other workloads:
-             the step between explicit pinned copies).  `e2e.ceiling` is a copy-only run of the same bytes.
+             FrameStep.run double-buffered between pinned copies on side streams).  `e2e.ceiling` is a copy-only run of
+             the same bytes.
 `roofline` : the dominant kernel against the measured HBM peak; `kernels` / `sweep`: per-kernel times and the
              sweep's FP32 figures; `frame_hbm_frac` counts the bytes of the launched (fused) configuration,
              `survey_hbm_frac` the SURVEY 8d accounting (every reference pass on its own).
@@ -630,23 +631,47 @@ def run_ours(args, dpv, wl):
         h2d, d2h = pipe.last_bytes()
         copy_in = [pins[0][k] for k in ("feats", "logits")]
     else:
-        pin_in = {k: v.cpu().pin_memory() for k, v in dsets[0].items()}
+        # Double-buffered through the public FrameStep API, as a streaming caller would: batch i + 1 is copied in on a
+        # copy stream while batch i computes; the results of batch i go back on a third stream and must have left
+        # the step's output buffers before batch i + 1 overwrites them.
+        if len(dsets) < 2:
+            dsets = dsets + [{k: torch.empty_like(v) for k, v in dsets[0].items()}]
+        pin_in = [{k: v.cpu().pin_memory() for k, v in dsets[0].items()} for _ in range(2)]
         run_step(dsets[0])
-        pin_out = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in results().items()}
-        h2d = sum(t.numel() * t.element_size() for t in pin_in.values())
-        d2h = sum(t.numel() * t.element_size() for t in pin_out.values())
+        pin_out = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in results().items()} for _ in range(2)]
+        h2d = sum(t.numel() * t.element_size() for t in pin_in[0].values())
+        d2h = sum(t.numel() * t.element_size() for t in pin_out[0].values())
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        mk_ev = lambda: [torch.cuda.Event() for _ in range(2)]
+        ev_in, ev_done, ev_out = mk_ev(), mk_ev(), mk_ev()
 
         def e2e_run(n):
-            for _ in range(n):
-                for k, t in pin_in.items():
-                    dsets[0][k].copy_(t, non_blocking=True)
-                run_step(dsets[0])
-                for k, t in results().items():
-                    pin_out[k].copy_(t, non_blocking=True)
-                torch.cuda.synchronize()
-        e2e_api = "%s.run between pinned-host copies of every input and result" % type(step).__name__
-        e2e_run(2)
-        copy_in = list(pin_in.values())
+            main = torch.cuda.current_stream()
+            for i in range(n):
+                j = i % 2
+                with torch.cuda.stream(s_in):
+                    if i >= 2:
+                        s_in.wait_event(ev_done[j])           # the step that last read input set j is done
+                    for k, t in pin_in[j].items():
+                        dsets[j][k].copy_(t, non_blocking=True)
+                    ev_in[j].record(s_in)
+                main.wait_event(ev_in[j])
+                if i >= 1:
+                    main.wait_event(ev_out[(i - 1) % 2])      # the previous results have left the output buffers
+                run_step(dsets[j])
+                ev_done[j].record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[j])
+                    if i >= 2:
+                        ev_out[j].synchronize()               # (host) pin_out[j] of batch i - 2 has been consumed
+                    for k, t in results().items():
+                        pin_out[j][k].copy_(t, non_blocking=True)
+                    ev_out[j].record(s_out)
+            torch.cuda.synchronize()
+        e2e_api = ("%s.run, double-buffered: pinned-host copies of every input (copy stream) and result (third stream) "
+                   "overlap the step" % type(step).__name__)
+        e2e_run(3)
+        copy_in = list(pin_in[0].values())
     barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
