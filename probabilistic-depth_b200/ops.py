@@ -548,9 +548,10 @@ class Base3DConvs:
             raise ValueError("the last layer must be the 32 -> 1 classifier")
         self._buf = None
 
-    @classmethod
-    def from_module(cls, m):
-        """m: a Base3D (the reference's or the mirror's): dres0, dres_modules (a plain list), classify."""
+    @staticmethod
+    def spec_from_module(m):
+        """The layer list of a Base3D (the reference's or the mirror's: dres0, dres_modules (a plain list), classify)
+        in the form __init__ and oracle.dpv_oracle.base3d take.  Pure Python: no device, no library."""
         def bn_of(bn):
             use_batch = bn.training or not bn.track_running_stats
             return dict(gamma=bn.weight, beta=bn.bias, mean=bn.running_mean, var=bn.running_var, eps=bn.eps,
@@ -562,7 +563,12 @@ class Base3DConvs:
             L.append(dict(weight=blk[2][0].weight, bn=bn_of(blk[2][1]), relu=False, block="out"))
         L.append(dict(weight=m.classify[0][0].weight, bn=bn_of(m.classify[0][1]), relu=True))
         L.append(dict(weight=m.classify[2].weight, bn=None, relu=False))
-        return cls(L)
+        return L
+
+    @classmethod
+    def from_module(cls, m):
+        """m: a Base3D (the reference's or the mirror's)."""
+        return cls(cls.spec_from_module(m))
 
     def __call__(self, volume, out=None):
         _need(volume, "volume")

@@ -102,3 +102,66 @@ def test_forward_matches_reference_outputs(name):
         np.testing.assert_allclose(dr, GOLD["%s_f%d_depth" % (name, f)], rtol=tol, atol=tol)
         # log-DPVs are normalised
         assert float((torch.logsumexp(refined, 1)).abs().max()) < 1e-4
+
+
+def _randomise_bn(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    for mod in list(m.modules()) + [x for b in m.dres_modules for x in b.modules()]:
+        if isinstance(mod, torch.nn.BatchNorm3d):
+            n = mod.num_features
+            mod.weight.data = 0.5 + torch.rand(n, generator=g)
+            mod.bias.data = 0.2 * torch.randn(n, generator=g)
+            if mod.running_mean is not None:
+                mod.running_mean.data = 0.1 * torch.randn(n, generator=g)
+                mod.running_var.data = 0.5 + torch.rand(n, generator=g)
+
+
+@pytest.mark.parametrize("bn_avg", [True, False])
+def test_base3d_layer_spec_describes_the_module(bn_avg):
+    """`Base3DConvs.spec_from_module` (what the tensor-core path is built from: weights, which BatchNorms fold and
+    which use batch statistics, ReLUs, residual blocks) evaluated by the float64 oracle reproduces the module's own
+    forward -- for the mirror Base3D in eval(), with running statistics (bn_avg true: dres0 / classify fold, the
+    unregistered residual blocks stay on batch statistics) and without (everything on batch statistics)."""
+    from oracle import dpv_oracle as O
+    OM = importlib.import_module("probabilistic-depth_b200.models.models")
+    ops = importlib.import_module("probabilistic-depth_b200.ops")
+    torch.manual_seed(3)
+    m = OM.Base3D(4, dres_count=2, feature_dim=32, bn_running_avg=bn_avg).eval()
+    _randomise_bn(m, 5)
+    spec = ops.Base3DConvs.spec_from_module(m)
+    assert [L.get("block") for L in spec] == [None, None, "in", "out", "in", "out", None, None]
+    assert [bool(L["bn"] and L["bn"]["batch_stats"]) for L in spec] == \
+        ([False, False, True, True, True, True, False, False] if bn_avg else [True] * 7 + [False])
+    vol = torch.randn((2, 4, 5, 6, 7), generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        want = m(vol)
+        got = O.base3d(vol, spec)
+    assert float((got - want.double()).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_base3d_layer_spec_describes_the_reference_module():
+    """The same for the reference's own Base3D (models/models.py:376-438), built on this GPU-less container with
+    nn.Module.cuda replaced by the identity for the duration of its constructor."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import dpv_oracle as O, reference_loader
+    ops = importlib.import_module("probabilistic-depth_b200.ops")
+    ref = reference_loader.load()
+    try:
+        real_cuda = torch.nn.Module.cuda
+        torch.nn.Module.cuda = lambda self, device=None: self
+        try:
+            torch.manual_seed(3)
+            m = ref.models.Base3D(4, dres_count=2, feature_dim=32, bn_running_avg=True, id=0).eval()
+        finally:
+            torch.nn.Module.cuda = real_cuda
+        _randomise_bn(m, 5)
+        spec = ops.Base3DConvs.spec_from_module(m)
+        vol = torch.randn((2, 4, 5, 6, 7), generator=torch.Generator().manual_seed(8))
+        with torch.no_grad():
+            want = m(vol, prob=False)
+            got = O.base3d(vol, spec)
+        assert float((got - want.double()).abs().max()) <= 1e-5 * float(want.abs().max())
+    finally:
+        reference_loader.restore()
