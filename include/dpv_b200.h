@@ -263,6 +263,9 @@ int dpv_conv3x3_d64(const float* in_hi, const float* in_lo, const float* w_hi, c
  *                            dres_modules of Base3D never leave training mode, models/models.py:394-399): raw, stats
  *                            -> (x - mean) / sqrt(biased var + eps) * gamma + beta, + residual, ReLU -> packed hi / lo.
  *                            Running statistics are not updated.
+ *   dpv_conv3d_c32_to1       the classifier Conv3d(c_in <= 32, 1, 3, 1, 1, bias=False) (models/models.py:403) on the FP32
+ *                            pipe: packed in -> [B,D,H,W].  weight_host: the torch weight [1][c_in][3][3][3] in HOST
+ *                            memory (864 floats at most; they travel as launch parameters).
  */
 int64_t dpv_conv3d_packed_floats(int B, int D, int H, int W);
 int dpv_conv3d_pack(const float* x, float* packed_hi, float* packed_lo, int B, int C, int D, int H, int W, void* stream);
@@ -271,6 +274,8 @@ int dpv_conv3d_pack_weights(const float* weight, const float* scale, float* w_hi
 int dpv_conv3d_c32(const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo, const float* shift,
                    const float* res_hi, const float* res_lo, float* out_hi, float* out_lo, float* out_c0,
                    float* out_raw, double* stats, int B, int D, int H, int W, int relu, int c_in, void* stream);
+int dpv_conv3d_c32_to1(const float* in_hi, const float* in_lo, const float* weight_host, float* out, int B, int D, int H,
+                       int W, int c_in, void* stream);
 int dpv_conv3d_bn_apply(const float* raw, const double* stats, const float* gamma, const float* beta, float eps,
                         const float* res_hi, const float* res_lo, float* out_hi, float* out_lo, int B, int D, int H,
                         int W, int relu, void* stream);

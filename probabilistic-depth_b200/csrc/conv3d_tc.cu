@@ -353,6 +353,60 @@ __global__ void __launch_bounds__(256) conv3d_bn_apply_kernel(const float* __res
     reinterpret_cast<float4*>(lo)[t] = l;
 }
 
+// The classifier, Conv3d(32, 1, 3, padding 1, bias=False) (models/models.py:403): one output channel is a dot product
+// of 864 terms per voxel -- nothing for a 128-row MMA whose cost does not shrink with N (section 4.6 of DESIGN.md), so it
+// runs on the FP32 pipe: 128 consecutive padded positions per CTA; per (dz, dy) pair the 130 rows the three dx taps need
+// are staged as value = hi + lo in shared memory, channel-major with a row stride of 131 floats (staging stores and
+// compute loads are both bank-conflict-free); the 864 weights travel as LAUNCH PARAMETERS, so every FMA takes its weight
+// from the constant bank and the inner loop is one LDS + one FFMA per term.
+constexpr int C1_TP = 128, C1_ROWS = C1_TP + 2, C1_STRIDE = 131;
+struct Conv1Weights { float w[27 * C3_C]; };      // [tap][input channel]
+__global__ void __launch_bounds__(C1_TP) conv3d_c32_to1_kernel(const float* __restrict__ in_hi, const float* __restrict__ in_lo,
+                                                               float* __restrict__ out, int B, int D, int H, int W,
+                                                               const __grid_constant__ Conv1Weights wt) {
+    __shared__ float s[C3_C * C1_STRIDE];
+    const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
+    const long long per = (long long)Dp * Hp * Wp, NP = (long long)B * per;
+    const long long p0 = (long long)blockIdx.x * C1_TP;
+    const int tid = threadIdx.x;
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 9; ++g) {
+        const long long r0 = p0 + (long long)(g / 3 - 1) * Hp * Wp + (g % 3 - 1) * Wp - 1;      // first staged row
+        // 130 rows x 8 float4: thread t takes float4 (t % 8) of rows t / 8, t / 8 + 16, ...
+        for (int i = tid; i < C1_ROWS * 8; i += C1_TP) {
+            const int row = i >> 3, c4 = i & 7;
+            const long long r = r0 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r >= 0 && r < NP) {
+                const float4 h = __ldg(reinterpret_cast<const float4*>(in_hi + r * C3_C) + c4);
+                const float4 l = __ldg(reinterpret_cast<const float4*>(in_lo + r * C3_C) + c4);
+                v = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+            }
+            float* d = s + (c4 * 4) * C1_STRIDE + row;
+            d[0] = v.x; d[C1_STRIDE] = v.y; d[2 * C1_STRIDE] = v.z; d[3 * C1_STRIDE] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < C3_C; ++c) {
+            const float* sc = s + c * C1_STRIDE + tid;
+            acc = fmaf(sc[0], wt.w[(g * 3 + 0) * C3_C + c], acc);
+            acc = fmaf(sc[1], wt.w[(g * 3 + 1) * C3_C + c], acc);
+            acc = fmaf(sc[2], wt.w[(g * 3 + 2) * C3_C + c], acc);
+        }
+        __syncthreads();
+    }
+    const long long p = p0 + tid;
+    if (p >= NP) return;
+    const long long b = p / per;
+    long long rem = p - b * per;
+    const int zp = (int)(rem / (Hp * Wp));
+    rem -= (long long)zp * (Hp * Wp);
+    const int yp = (int)rem / Wp, xp = (int)rem - yp * Wp;
+    if (zp >= 1 && zp <= D && yp >= 1 && yp <= H && xp >= 1 && xp <= W)
+        out[((b * D + (zp - 1)) * H + (yp - 1)) * W + (xp - 1)] = acc;
+}
+
 // torch weight [C_out][C_in][3][3][3] (C_out, C_in <= 32), optional per-output-channel scale (the folded BatchNorm)
 // -> packed hi / lo [27 taps][32 out][32 in], zero where out >= C_out or in >= C_in.
 __global__ void __launch_bounds__(256) conv3d_pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ scale,
@@ -463,6 +517,22 @@ extern "C" int dpv_conv3d_bn_apply(const float* raw, const double* stats, const 
     const long long n = (long long)B * (D + 2) * (H + 2) * (W + 2);
     conv3d_bn_apply_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, stats, gamma, beta, eps, res_hi,
                                                                                        res_lo, out_hi, out_lo, B, D, H, W, relu ? 1 : 0);
+    DPV_LAUNCH_END();
+    return 0;
+}
+
+extern "C" int dpv_conv3d_c32_to1(const float* in_hi, const float* in_lo, const float* weight_host, float* out, int B, int D,
+                                  int H, int W, int c_in, void* stream) {
+    using namespace dpv;
+    DPV_CHECK_ARG(in_hi && in_lo && weight_host && out && B > 0 && D > 0 && H > 0 && W > 0);
+    DPV_CHECK_ARG(c_in > 0 && c_in <= C3_C);
+    if (((uintptr_t)in_hi | (uintptr_t)in_lo) & 15) return DPV_E_BADARG;
+    const long long np = (long long)B * (D + 2) * (H + 2) * (W + 2);
+    if (np > (1LL << 31) - 4096) return DPV_E_UNSUPP;
+    Conv1Weights wt;                                 // torch layout [1][c_in][3][3][3] -> [tap][32], zero beyond c_in
+    for (int t = 0; t < 27; ++t)
+        for (int c = 0; c < C3_C; ++c) wt.w[t * C3_C + c] = c < c_in ? weight_host[c * 27 + t] : 0.f;
+    conv3d_c32_to1_kernel<<<(unsigned)((np + C1_TP - 1) / C1_TP), C1_TP, 0, (cudaStream_t)stream>>>(in_hi, in_lo, out, B, D, H, W, wt);
     DPV_LAUNCH_END();
     return 0;
 }

@@ -542,10 +542,16 @@ class Base3DConvs:
             hi = torch.empty((27, 32, 32), device=w.device, dtype=torch.float32)
             lo = torch.empty_like(hi)
             _lib.check(lib.dpv_conv3d_pack_weights(_p(w.contiguous().float()), _p(scale), _p(hi), _p(lo), co, ci, _stream()))
+            # the 32 -> 1 classifier runs on the FP32 pipe with its weights as launch parameters (host copy, once)
+            w_host = None
+            if co == 1 and bn is None and not L.get("relu") and L.get("block") is None:
+                w_host = np.ascontiguousarray(w.float().cpu().numpy().reshape(-1))
             self.layers.append(dict(w=(hi, lo), shift=shift, gamma=gamma, beta=beta, eps=eps, batch_stats=batch_stats,
-                                    relu=bool(L.get("relu", False)), block=L.get("block"), co=co, ci=ci))
+                                    relu=bool(L.get("relu", False)), block=L.get("block"), co=co, ci=ci, w_host=w_host))
         if self.layers[-1]["co"] != 1:
             raise ValueError("the last layer must be the 32 -> 1 classifier")
+        import os
+        self.last_on_fp32_pipe = os.environ.get("DPV_BASE3D_LAST_TC", "0") != "1"    # (1: the tensor-core kernel, for timing)
         self._buf = None
 
     @staticmethod
@@ -599,7 +605,10 @@ class Base3DConvs:
             res = skip if L["block"] == "out" else None
             dst = (None, None) if last else next(b for b in bufs if b is not cur and b is not skip)
             hi, lo = L["w"]
-            if L["batch_stats"]:
+            if last and L["w_host"] is not None and self.last_on_fp32_pipe:
+                _lib.check(lib.dpv_conv3d_c32_to1(_p(cur[0]), _p(cur[1]), L["w_host"].ctypes.data, _p(out), B, D, H, W,
+                                                  L["ci"], st))
+            elif L["batch_stats"]:
                 _lib.check(lib.dpv_conv3d_c32(_p(cur[0]), _p(cur[1]), _p(hi), _p(lo), None, None, None, None, None, None,
                                               _p(raw), stats[i].data_ptr(), B, D, H, W, 0, L["ci"], st))
                 _lib.check(lib.dpv_conv3d_bn_apply(_p(raw), stats[i].data_ptr(), _p(L["gamma"]), _p(L["beta"]), L["eps"],
