@@ -510,7 +510,8 @@ class Base3DConvs:
     that uses batch statistics (training mode -- the reference's unregistered dres_modules never leave it -- or
     track_running_stats = False) is computed from sums the convolution's epilogue accumulates (running statistics
     are NOT updated by this path).  Built once per model with `from_module`; `__call__(volume)` returns the
-    residual [B, D, h, w] (`prob=False` in the reference)."""
+    residual [B, D, h, w] (`prob=False` in the reference).  The packed activations and the statistics live in buffers
+    the object owns (re-used call after call, sized by the first call's shape): one call in flight per object."""
 
     def __init__(self, layers):
         """layers: list of dicts {weight [Co,Ci,3,3,3], bn: None | dict(gamma, beta, mean, var, eps, batch_stats),
