@@ -258,7 +258,13 @@ int dpv_conv3x3_d64(const float* in_hi, const float* in_lo, const float* w_hi, c
  *                            32 -> 1 classifier, models/models.py:403); out_raw [positions][32] fp32 together with
  *                            stats (double[64], caller-zeroed: per channel sum and sum of squares over the real
  *                            voxels, +=) for a BatchNorm that uses BATCH statistics.  c_in = real input channels
- *                            (K steps beyond them are skipped).
+ *                            (K steps beyond them are skipped).  relu: bit 0 = ReLU; bit 2 = the input and the filter
+ *                            are z-folded (below; c_in = 3 x the layer's input channels).
+ *   dpv_conv3d_pack_zfold, dpv_conv3d_pack_weights_zfold
+ *                            a first layer with 3 C_in <= 32 input channels: the packed input holds, per position, the
+ *                            C_in channels of the three z-planes z-1, z, z+1 (channel dzi * C_in + c), the filter is
+ *                            packed to match ([dy*3+dx][out][dzi * C_in + c]); the convolution over dz becomes part of
+ *                            the channel contraction (3 K-blocks instead of 9: a third of the copies).
  *   dpv_conv3d_bn_apply      BatchNorm with batch statistics (F.batch_norm(training=True): the unregistered
  *                            dres_modules of Base3D never leave training mode, models/models.py:394-399): raw, stats
  *                            -> (x - mean) / sqrt(biased var + eps) * gamma + beta, + residual, ReLU -> packed hi / lo.
@@ -274,6 +280,10 @@ int dpv_conv3d_pack_weights(const float* weight, const float* scale, float* w_hi
 int dpv_conv3d_c32(const float* in_hi, const float* in_lo, const float* w_hi, const float* w_lo, const float* shift,
                    const float* res_hi, const float* res_lo, float* out_hi, float* out_lo, float* out_c0,
                    float* out_raw, double* stats, int B, int D, int H, int W, int relu, int c_in, void* stream);
+int dpv_conv3d_pack_zfold(const float* x, float* packed_hi, float* packed_lo, int B, int C, int D, int H, int W,
+                          void* stream);
+int dpv_conv3d_pack_weights_zfold(const float* weight, const float* scale, float* w_hi, float* w_lo, int C_out, int C_in,
+                                  void* stream);
 int dpv_conv3d_c32_to1(const float* in_hi, const float* in_lo, const float* weight_host, float* out, int B, int D, int H,
                        int W, int c_in, void* stream);
 int dpv_conv3d_bn_apply(const float* raw, const double* stats, const float* gamma, const float* beta, float eps,

@@ -46,6 +46,8 @@ PROTOTYPES = {
     "dpv_conv3d_pack": (_c_i, [_c_fp] * 3 + [_c_i] * 5 + [_c_fp]),
     "dpv_conv3d_pack_weights": (_c_i, [_c_fp] * 4 + [_c_i] * 2 + [_c_fp]),
     "dpv_conv3d_c32": (_c_i, [_c_fp] * 12 + [_c_i] * 6 + [_c_fp]),
+    "dpv_conv3d_pack_zfold": (_c_i, [_c_fp] * 3 + [_c_i] * 5 + [_c_fp]),
+    "dpv_conv3d_pack_weights_zfold": (_c_i, [_c_fp] * 4 + [_c_i] * 2 + [_c_fp]),
     "dpv_conv3d_c32_to1": (_c_i, [_c_fp] * 4 + [_c_i] * 5 + [_c_fp]),
     "dpv_conv3d_bn_apply": (_c_i, [_c_fp] * 4 + [_c_f] + [_c_fp] * 4 + [_c_i] * 5 + [_c_fp]),
     "dpv_depth_errors_workspace_doubles": (_c_i64, [_c_i] * 3),

@@ -60,6 +60,7 @@ struct Conv3Args {
     int B, D, H, W;
     long long NP;                      // B * (D+2) * (H+2) * (W+2)
     int relu, ksteps;
+    int nkb, zfold;                    // K-blocks per tile: 9 (dz, dy) pairs, or 3 dy rows when the input is z-folded
 };
 
 __global__ void __launch_bounds__(C3_THREADS, 1)
@@ -95,10 +96,10 @@ conv3d_c32_tc_kernel(const Conv3Args a, const __grid_constant__ Conv3Maps maps) 
             int g = 0;
             for (int pass = blockIdx.x; pass < npass; pass += gridDim.x) {
                 const long long p0 = (long long)pass * (C3_MT * C3_M);
-                for (int kb = 0; kb < C3_NKB; ++kb, ++g) {
+                for (int kb = 0; kb < a.nkb; ++kb, ++g) {
                     const int s = g % C3_STAGES, use = g / C3_STAGES;
                     if (use > 0) tm_mbar_wait(&empty_bar[s], (use - 1) & 1);
-                    const int dz = kb / 3 - 1, dy = kb % 3 - 1;
+                    const int dz = a.zfold ? 0 : kb / 3 - 1, dy = a.zfold ? kb - 1 : kb % 3 - 1;
                     unsigned char* st = stage0 + s * C3_STAGE_BYTES;
                     tm_mbar_expect_tx(&full_bar[s], C3_STAGE_BYTES);
                     // the dx = -1 tap's first row; rows < 0 or >= NP are zero-filled.  |row| < 2^31 is checked by the host.
@@ -128,7 +129,7 @@ conv3d_c32_tc_kernel(const Conv3Args a, const __grid_constant__ Conv3Maps maps) 
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const unsigned tmem_t = tmem_d + (unsigned)(buf * C3_COLS);
-                for (int kb = 0; kb < C3_NKB; ++kb, ++g) {
+                for (int kb = 0; kb < a.nkb; ++kb, ++g) {
                     const int s = g % C3_STAGES, use = g / C3_STAGES;
                     tm_mbar_wait(&full_bar[s], use & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -297,6 +298,56 @@ __global__ void __launch_bounds__(256) conv3d_pack_kernel(const float* __restric
     l.x = ct_hi(v[0] - h.x); l.y = ct_hi(v[1] - h.y); l.z = ct_hi(v[2] - h.z); l.w = ct_hi(v[3] - h.w);
     reinterpret_cast<float4*>(hi)[t] = h;
     reinterpret_cast<float4*>(lo)[t] = l;
+}
+
+// The first layer's input, z-folded: channel dzi * C + c of position (z, y, x) holds x[c] at (z + dzi - 1, y, x)
+// (3 C <= 32; zero outside the volume).  The convolution over dz then is part of the channel contraction: 3 K-blocks
+// (dy) of two K steps instead of 9 of one -- a third of the copies for a layer whose cost is its copies.
+__global__ void __launch_bounds__(256) conv3d_pack_zfold_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                                float* __restrict__ lo, int B, int C, int D, int H, int W) {
+    const int Wp = W + 2, Hp = H + 2, Dp = D + 2;
+    const long long per = (long long)Dp * Hp * Wp;
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long p = t >> 3;
+    const int k0 = (int)(t & 7) * 4;
+    if (p >= (long long)B * per) return;
+    const long long b = p / per;
+    long long rem = p - b * per;
+    const int zp = (int)(rem / (Hp * Wp));
+    rem -= (long long)zp * (Hp * Wp);
+    const int yp = (int)rem / Wp, xp = (int)rem - yp * Wp;
+    const bool real = zp >= 1 && zp <= D && yp >= 1 && yp <= H && xp >= 1 && xp <= W;
+    const long long DHW = (long long)D * H * W, HW = (long long)H * W;
+    const float* src = x + b * C * DHW + (long long)(yp - 1) * W + (xp - 1);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = k0 + j, dzi = k / C, c = k - dzi * C;
+        const int z = zp - 1 + dzi - 1;
+        v[j] = (real && dzi < 3 && z >= 0 && z < D) ? __ldg(src + c * DHW + z * HW) : 0.f;
+    }
+    float4 h, l;
+    h.x = ct_hi(v[0]); h.y = ct_hi(v[1]); h.z = ct_hi(v[2]); h.w = ct_hi(v[3]);
+    l.x = ct_hi(v[0] - h.x); l.y = ct_hi(v[1] - h.y); l.z = ct_hi(v[2] - h.z); l.w = ct_hi(v[3] - h.w);
+    reinterpret_cast<float4*>(hi)[t] = h;
+    reinterpret_cast<float4*>(lo)[t] = l;
+}
+
+// The matching filter: tap slot dy * 3 + dx (the first 9 of 27), input channel dzi * C_in + c.
+__global__ void __launch_bounds__(256) conv3d_pack_weights_zfold_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                                                        float* __restrict__ hi, float* __restrict__ lo,
+                                                                        int C_out, int C_in) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= 27 * C3_C * C3_C) return;
+    const int k = i % C3_C, o = (i / C3_C) % C3_C, t = i / (C3_C * C3_C);
+    const int dzi = k / C_in, c = k - dzi * C_in;
+    float v = 0.f;
+    if (t < 9 && o < C_out && dzi < 3) {
+        v = __ldg(w + ((long long)o * C_in + c) * 27 + dzi * 9 + t);
+        if (scale != nullptr) v = __fmul_rn(v, __ldg(scale + o));
+    }
+    const float h = ct_hi(v);
+    hi[i] = h; lo[i] = ct_hi(v - h);
 }
 
 // BatchNorm3d with BATCH statistics (training mode, or track_running_stats = False: torch.nn.functional.batch_norm
@@ -488,7 +539,9 @@ extern "C" int dpv_conv3d_c32(const float* in_hi, const float* in_lo, const floa
     Conv3Args a;
     a.bias = shift; a.res_hi = res_hi; a.res_lo = res_lo; a.out_hi = out_hi; a.out_lo = out_lo; a.out_c0 = out_c0;
     a.out_raw = out_raw; a.stats = stats;
-    a.B = B; a.D = D; a.H = H; a.W = W; a.NP = np; a.relu = relu ? 1 : 0;
+    a.B = B; a.D = D; a.H = H; a.W = W; a.NP = np; a.relu = (relu & 1) ? 1 : 0;
+    a.zfold = (relu & 4) ? 1 : 0;
+    a.nkb = a.zfold ? 3 : C3_NKB;
     a.ksteps = (c_in + 7) / 8;
     const size_t smem = (size_t)C3_STAGES * C3_STAGE_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(conv3d_c32_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -533,6 +586,28 @@ extern "C" int dpv_conv3d_c32_to1(const float* in_hi, const float* in_lo, const 
     for (int t = 0; t < 27; ++t)
         for (int c = 0; c < C3_C; ++c) wt.w[t * C3_C + c] = c < c_in ? weight_host[c * 27 + t] : 0.f;
     conv3d_c32_to1_kernel<<<(unsigned)((np + C1_TP - 1) / C1_TP), C1_TP, 0, (cudaStream_t)stream>>>(in_hi, in_lo, out, B, D, H, W, wt);
+    DPV_LAUNCH_END();
+    return 0;
+}
+
+extern "C" int dpv_conv3d_pack_zfold(const float* x, float* packed_hi, float* packed_lo, int B, int C, int D, int H, int W,
+                                     void* stream) {
+    using namespace dpv;
+    DPV_CHECK_ARG(x && packed_hi && packed_lo && B > 0 && D > 0 && H > 0 && W > 0 && C > 0);
+    if (3 * C > C3_C) return DPV_E_UNSUPP;
+    const long long n = (long long)B * (D + 2) * (H + 2) * (W + 2);
+    if (n > (1LL << 31) - 4096) return DPV_E_UNSUPP;
+    conv3d_pack_zfold_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, packed_hi, packed_lo, B, C, D, H, W);
+    DPV_LAUNCH_END();
+    return 0;
+}
+
+extern "C" int dpv_conv3d_pack_weights_zfold(const float* weight, const float* scale, float* w_hi, float* w_lo, int C_out,
+                                             int C_in, void* stream) {
+    using namespace dpv;
+    DPV_CHECK_ARG(weight && w_hi && w_lo && C_out > 0 && C_in > 0);
+    if (C_out > C3_C || 3 * C_in > C3_C) return DPV_E_UNSUPP;
+    conv3d_pack_weights_zfold_kernel<<<(27 * C3_C * C3_C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, scale, w_hi, w_lo, C_out, C_in);
     DPV_LAUNCH_END();
     return 0;
 }

@@ -518,8 +518,9 @@ class Base3DConvs:
         relu: bool, block: None | "in" | "out"} -- "in" marks the first layer of a residual block (its input is the
         skip), "out" the layer whose result the skip is added to."""
         lib = _lib.load()
+        import os
         self.layers = []
-        for L in layers:
+        for li, L in enumerate(layers):
             w = L["weight"].detach()
             _need(w, "weight")
             co, ci = int(w.shape[0]), int(w.shape[1])
@@ -542,16 +543,19 @@ class Base3DConvs:
                     shift = _pad32((b.double() - bn["mean"].detach().double() * sc).float(), 0.0)
             hi = torch.empty((27, 32, 32), device=w.device, dtype=torch.float32)
             lo = torch.empty_like(hi)
-            _lib.check(lib.dpv_conv3d_pack_weights(_p(w.contiguous().float()), _p(scale), _p(hi), _p(lo), co, ci, _stream()))
+            # a first layer with few input channels is z-folded: the three z-planes become channels (a third of the copies)
+            zfold = li == 0 and 3 * ci <= 32 and os.environ.get("DPV_BASE3D_ZFOLD", "1") != "0"
+            pack_w = lib.dpv_conv3d_pack_weights_zfold if zfold else lib.dpv_conv3d_pack_weights
+            _lib.check(pack_w(_p(w.contiguous().float()), _p(scale), _p(hi), _p(lo), co, ci, _stream()))
             # the 32 -> 1 classifier runs on the FP32 pipe with its weights as launch parameters (host copy, once)
             w_host = None
             if co == 1 and bn is None and not L.get("relu") and L.get("block") is None:
                 w_host = np.ascontiguousarray(w.float().cpu().numpy().reshape(-1))
             self.layers.append(dict(w=(hi, lo), shift=shift, gamma=gamma, beta=beta, eps=eps, batch_stats=batch_stats,
-                                    relu=bool(L.get("relu", False)), block=L.get("block"), co=co, ci=ci, w_host=w_host))
+                                    relu=bool(L.get("relu", False)), block=L.get("block"), co=co, ci=ci, w_host=w_host,
+                                    zfold=zfold))
         if self.layers[-1]["co"] != 1:
             raise ValueError("the last layer must be the 32 -> 1 classifier")
-        import os
         self.last_on_fp32_pipe = os.environ.get("DPV_BASE3D_LAST_TC", "0") != "1"    # (1: the tensor-core kernel, for timing)
         self._buf = None
 
@@ -596,7 +600,8 @@ class Base3DConvs:
         if raw is not None:
             stats.zero_()
         cur = bufs[0]
-        _lib.check(lib.dpv_conv3d_pack(_p(volume), _p(cur[0]), _p(cur[1]), B, C, D, H, W, st))
+        pack = lib.dpv_conv3d_pack_zfold if self.layers[0]["zfold"] else lib.dpv_conv3d_pack
+        _lib.check(pack(_p(volume), _p(cur[0]), _p(cur[1]), B, C, D, H, W, st))
         out = torch.empty((B, D, H, W), device=volume.device, dtype=torch.float32) if out is None else out
         skip = None
         for i, L in enumerate(self.layers):
@@ -606,12 +611,13 @@ class Base3DConvs:
             res = skip if L["block"] == "out" else None
             dst = (None, None) if last else next(b for b in bufs if b is not cur and b is not skip)
             hi, lo = L["w"]
+            zf, cin = (4, 3 * L["ci"]) if L["zfold"] else (0, L["ci"])
             if last and L["w_host"] is not None and self.last_on_fp32_pipe:
                 _lib.check(lib.dpv_conv3d_c32_to1(_p(cur[0]), _p(cur[1]), L["w_host"].ctypes.data, _p(out), B, D, H, W,
                                                   L["ci"], st))
             elif L["batch_stats"]:
                 _lib.check(lib.dpv_conv3d_c32(_p(cur[0]), _p(cur[1]), _p(hi), _p(lo), None, None, None, None, None, None,
-                                              _p(raw), stats[i].data_ptr(), B, D, H, W, 0, L["ci"], st))
+                                              _p(raw), stats[i].data_ptr(), B, D, H, W, zf, cin, st))
                 _lib.check(lib.dpv_conv3d_bn_apply(_p(raw), stats[i].data_ptr(), _p(L["gamma"]), _p(L["beta"]), L["eps"],
                                                    _p(res[0]) if res else None, _p(res[1]) if res else None,
                                                    _p(dst[0]), _p(dst[1]), B, D, H, W, 1 if L["relu"] else 0, st))
@@ -619,7 +625,7 @@ class Base3DConvs:
                 _lib.check(lib.dpv_conv3d_c32(_p(cur[0]), _p(cur[1]), _p(hi), _p(lo), _p(L["shift"]),
                                               _p(res[0]) if res else None, _p(res[1]) if res else None,
                                               _p(dst[0]), _p(dst[1]), _p(out) if last else None, None, None,
-                                              B, D, H, W, 1 if L["relu"] else 0, L["ci"], st))
+                                              B, D, H, W, (1 if L["relu"] else 0) | zf, cin, st))
             if L["block"] == "out":
                 skip = None
             cur = dst
