@@ -23,7 +23,10 @@
 //   * Epilogue (warps 2-5, one voxel per thread, 32 channels in registers): + shift, + residual (the packed
 //     activation of an earlier layer, hi + lo), ReLU, then either the re-split into the next layer's packed hi / lo
 //     or channel 0 of the last layer to [B][D][H][W].
-//   * The first layer has 4 real input channels of 32: only the first K step is issued (`ksteps`).
+//   * The first layer (4 real input channels) is z-folded (conv3d_pack_zfold_kernel): the three z-planes become 12 input
+//     channels, 3 K-blocks (dy) of two K steps instead of 9 of one.  Unfolded inputs with fewer than 32 channels
+//     issue only the K steps that hold data (`ksteps`).
+//   * The last layer (32 -> 1) runs on the FP32 pipe (conv3d_c32_to1_kernel below).
 #include <cuda.h>
 
 #include <cstdlib>
