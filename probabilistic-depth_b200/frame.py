@@ -117,6 +117,8 @@ class FrameStep:
                                             3 * h * w, st))
             hk("warp_feature", 1)
             if self.base3d is not None:
+                if prev is None or tuple(prev.shape) != (B, D, h, w):
+                    raise ValueError("feedback step with base3d: prev [B,D,h,w] (the previous frame's 1/4-res hand-off) is required")
                 hk("base3d", 0)
                 self.comb[:, 0].copy_(self.bv)                 # models/models.py:692: cat(BV_cur, prev_output, warped)
                 self.comb[:, 1].copy_(prev)

@@ -494,7 +494,12 @@ class CostRefine:
             _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
                                            None, None, _p(logits), B, H, W, 0, 0.0, st))
         if want_logp:
-            out = torch.empty_like(cost) if out is None else out
+            if out is None:
+                out = torch.empty_like(cost)
+            else:
+                _need(out, "out")
+                if tuple(out.shape) != tuple(cost.shape) or not out.is_contiguous() or out.device != cost.device:
+                    raise ValueError("out must be a contiguous tensor of the cost volume's shape on its device")
             _lib.check(lib.dpv_conv3x3_d64(_p(a_hi), _p(a_lo), _p(self.w[2][0]), _p(self.w[2][1]), _p(self.b[2]),
                                            None, None, _p(out), B, H, W, 2, 0.0, st))
         if want_logits and want_logp:
@@ -602,7 +607,12 @@ class Base3DConvs:
         cur = bufs[0]
         pack = lib.dpv_conv3d_pack_zfold if self.layers[0]["zfold"] else lib.dpv_conv3d_pack
         _lib.check(pack(_p(volume), _p(cur[0]), _p(cur[1]), B, C, D, H, W, st))
-        out = torch.empty((B, D, H, W), device=volume.device, dtype=torch.float32) if out is None else out
+        if out is None:
+            out = torch.empty((B, D, H, W), device=volume.device, dtype=torch.float32)
+        else:
+            _need(out, "out")
+            if tuple(out.shape) != (B, D, H, W) or not out.is_contiguous() or out.device != volume.device:
+                raise ValueError("out must be a contiguous [B, D, H, W] tensor on the volume's device")
         skip = None
         for i, L in enumerate(self.layers):
             last = i == len(self.layers) - 1
