@@ -275,6 +275,20 @@ conv3d_c32_tc_kernel(const Conv3Args a, const __grid_constant__ Conv3Maps maps) 
     }
 }
 
+// Position decode for the elementwise kernels: the host guarantees fewer than 2^31 positions, so 32-bit divisions do.
+struct C3Pos { unsigned b; int zp, yp, xp; };
+__device__ __forceinline__ C3Pos c3_decode(unsigned p, int Dp, int Hp, int Wp) {
+    C3Pos r;
+    const unsigned plane = (unsigned)(Hp * Wp), per = (unsigned)Dp * plane;
+    r.b = p / per;
+    unsigned rem = p - r.b * per;
+    r.zp = (int)(rem / plane);
+    rem -= (unsigned)r.zp * plane;
+    r.yp = (int)(rem / (unsigned)Wp);
+    r.xp = (int)(rem - (unsigned)r.yp * (unsigned)Wp);
+    return r;
+}
+
 // NCDHW fp32 [B][C][D][H][W] (C <= 32) -> packed hi / lo [B][D+2][H+2][W+2][32], zero border, channels >= C zero.
 // One thread per (position, group of 4 channels): the packed stores of a warp are 512 contiguous bytes.
 __global__ void __launch_bounds__(256) conv3d_pack_kernel(const float* __restrict__ x, float* __restrict__ hi,
@@ -285,11 +299,9 @@ __global__ void __launch_bounds__(256) conv3d_pack_kernel(const float* __restric
     const long long p = t >> 3;
     const int c = (int)(t & 7) * 4;
     if (p >= (long long)B * per) return;
-    const long long b = p / per;
-    long long rem = p - b * per;
-    const int zp = (int)(rem / (Hp * Wp));
-    rem -= (long long)zp * (Hp * Wp);
-    const int yp = (int)rem / Wp, xp = (int)rem - yp * Wp;
+    const C3Pos q = c3_decode((unsigned)p, Dp, Hp, Wp);
+    const long long b = q.b;
+    const int zp = q.zp, yp = q.yp, xp = q.xp;
     const bool real = zp >= 1 && zp <= D && yp >= 1 && yp <= H && xp >= 1 && xp <= W;
     const long long DHW = (long long)D * H * W;
     const float* src = x + b * C * DHW + ((long long)(zp - 1) * H + (yp - 1)) * W + (xp - 1);
@@ -314,20 +326,18 @@ __global__ void __launch_bounds__(256) conv3d_pack_zfold_kernel(const float* __r
     const long long p = t >> 3;
     const int k0 = (int)(t & 7) * 4;
     if (p >= (long long)B * per) return;
-    const long long b = p / per;
-    long long rem = p - b * per;
-    const int zp = (int)(rem / (Hp * Wp));
-    rem -= (long long)zp * (Hp * Wp);
-    const int yp = (int)rem / Wp, xp = (int)rem - yp * Wp;
+    const C3Pos q = c3_decode((unsigned)p, Dp, Hp, Wp);
+    const long long b = q.b;
+    const int zp = q.zp, yp = q.yp, xp = q.xp;
     const bool real = zp >= 1 && zp <= D && yp >= 1 && yp <= H && xp >= 1 && xp <= W;
     const long long DHW = (long long)D * H * W, HW = (long long)H * W;
     const float* src = x + b * C * DHW + (long long)(yp - 1) * W + (xp - 1);
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int k = k0 + j, dzi = k / C, c = k - dzi * C;
+        const int k = k0 + j, dzi = (k >= C) + (k >= 2 * C), c = k - dzi * C;      // (k < 3 C: no division)
         const int z = zp - 1 + dzi - 1;
-        v[j] = (real && dzi < 3 && z >= 0 && z < D) ? __ldg(src + c * DHW + z * HW) : 0.f;
+        v[j] = (real && k < 3 * C && z >= 0 && z < D) ? __ldg(src + c * DHW + z * HW) : 0.f;
     }
     float4 h, l;
     h.x = ct_hi(v[0]); h.y = ct_hi(v[1]); h.z = ct_hi(v[2]); h.w = ct_hi(v[3]);
@@ -382,11 +392,9 @@ __global__ void __launch_bounds__(256) conv3d_bn_apply_kernel(const float* __res
     const long long p = t >> 3;
     const int c = (int)(t & 7) * 4;
     if (p >= (long long)B * per) return;
-    const long long b = p / per;
-    long long rem = p - b * per;
-    const int zp = (int)(rem / (Hp * Wp));
-    rem -= (long long)zp * (Hp * Wp);
-    const int yp = (int)rem / Wp, xp = (int)rem - yp * Wp;
+    const C3Pos q = c3_decode((unsigned)p, Dp, Hp, Wp);
+    const long long b = q.b;
+    const int zp = q.zp, yp = q.yp, xp = q.xp;
     const bool real = zp >= 1 && zp <= D && yp >= 1 && yp <= H && xp >= 1 && xp <= W;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (real) {
